@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200-native FastSpeech2 + HiFi-GAN inference path (driver contract in the task brief).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference [...]                          CPU reference arm (oracle port of the reference, host cores)
+
+A "step" is one pass of the hot path over one synthetic batch per GPU: FastSpeech2.forward (phonemes -> mel, including the
+single host sync on max(mel_len)) followed by hifigan Generator.forward (mel -> 22.05 kHz fp32 waveform), i.e.
+BASELINE.json configs[2]; the mel-only configs[1] number is reported in `extra`.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HOP = 256
+FS2_FLOPS = lambda L, T: 4 * L * (5767168 + 1024 * L) + 2360832 * L + 6 * T * (5767168 + 1024 * T) + 8724480 * T
+HIFIGAN_FLOPS_PER_FRAME = 614105088
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step")
+    ap.add_argument("--phonemes", type=int, default=128)
+    ap.add_argument("--cpu-sample", type=int, default=2, help="utterances in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = os.path.join(tempfile.mkdtemp(), "clocks.csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def workload_config(args, world, frames_per_utt):
+    return {"workload": f"configs[2]: LJSpeech config, batch={args.batch}/GPU x {args.phonemes} phonemes -> ~{frames_per_utt:.0f} mel frames "
+                        "each (free-running, duration-steered random-init weights), FastSpeech2 + HiFi-GAN end to end, fp32 22.05 kHz waveform",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "phonemes": args.phonemes,
+            "mel_frames_per_utt": round(frames_per_utt, 1),
+            "parallelism": f"dp{world}: utterance shards, weights replicated, no data-path collective; NCCL all-gather of the waveforms only",
+            "l2": "per-step activation working set (>2 GB) and weights (196 MB) exceed the 126 MB L2; no explicit flush"}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(args, n_utt, steps, warmup):
+    """The reference's CPU implementation of the path (oracle port: the same ATen CPU kernels the reference calls),
+    all host threads, on a bounded sample of the workload.  Returns (samples/s, frames/s, seconds/step, cores, frames)."""
+    import torch
+    from fastspeech2_b200 import configs, synth
+    from oracle import fs2_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pc, mc = configs.make_configs("LJSpeech", tempfile.mkdtemp())
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=0)
+    hsd = O.fold_weight_norm(synth.hifigan_state_dict(configs.HIFIGAN_CONFIG, seed=0))
+    spk, texts, lens, L = synth.make_batch(args.batch, args.phonemes, seed=0)
+    spk, texts, lens = spk[:n_utt], texts[:n_utt], lens[:n_utt]
+
+    def step():
+        out = O.fastspeech2_forward(sd, spk, texts, lens, L)
+        t1 = time.perf_counter()
+        wav = O.hifigan_forward(hsd, out[1].transpose(1, 2))
+        return int(out[9].sum()), t1, wav
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    frames = 0
+    fs2_s = 0.0
+    for _ in range(steps):
+        ts = time.perf_counter()
+        f, t1, _ = step()
+        fs2_s += t1 - ts
+        frames += f
+    dt = time.perf_counter() - t0
+    return frames * HOP / dt, frames / max(fs2_s, 1e-9), dt / steps, cores, frames // steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(1, min(args.cpu_sample, args.batch))
+    sps, fps, sec, cores, frames = cpu_reference_run(args, n, args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "audio_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1, frames / n),
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} of the {args.batch} utterances per step ({frames} mel frames), oracle port of the reference "
+                                       "(same ATen CPU kernels), fp32, all host threads"},
+            "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extra": {"mel_frames_per_s_fastspeech2_only": fps}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from fastspeech2_b200 import _lib, configs, synth
+    from fastspeech2_b200.hifigan import AttrDict, Generator
+    from fastspeech2_b200.model import FastSpeech2
+    from fastspeech2_b200.parallel import gather_padded
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lib = _lib.lib()
+
+    pc, mc = configs.make_configs("LJSpeech", tempfile.mkdtemp())
+    model = FastSpeech2(pc, mc)
+    model.load_state_dict(synth.fastspeech2_state_dict(pc, mc, seed=0))
+    model = model.to(dev).eval()
+    voc = Generator(AttrDict(configs.HIFIGAN_CONFIG))
+    voc.load_state_dict(synth.hifigan_state_dict(configs.HIFIGAN_CONFIG, seed=0))
+    voc.eval()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        voc.remove_weight_norm()
+    voc.to(dev)
+
+    spk_h, texts_h, lens_h, L = synth.make_batch(args.batch, args.phonemes, seed=rank)
+    spk_h, texts_h, lens_h = spk_h.pin_memory(), texts_h.pin_memory(), lens_h.pin_memory()
+    spk, texts, lens = spk_h.to(dev), texts_h.to(dev), lens_h.to(dev)
+
+    def step_device():
+        out = model(spk, texts, lens, L)
+        wav = voc(out[1].transpose(1, 2))
+        if world > 1:
+            gather_padded(wav[:, 0], out[9])
+        return out, wav
+
+    def step_mel_only():
+        return model(spk, texts, lens, L)
+
+    wav_host = {}
+
+    def step_e2e():
+        s_d, t_d, l_d = spk_h.to(dev, non_blocking=True), texts_h.to(dev, non_blocking=True), lens_h.to(dev, non_blocking=True)
+        out = model(s_d, t_d, l_d, L)
+        wav = voc(out[1].transpose(1, 2))
+        if world > 1:
+            gather_padded(wav[:, 0], out[9])
+        key = tuple(wav.shape)
+        if key not in wav_host:
+            wav_host[key] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
+        wav_host[key].copy_(wav, non_blocking=True)
+        mel_lens_host = out[9].cpu()          # the step's result lengths (also the stream sync for the waveform copy)
+        return out, wav, mel_lens_host
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.fs2_kernel_launch_count()
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        launches = torch.tensor([lib.fs2_kernel_launch_count() - n0], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        return ms.item(), int(launches.item()), last
+
+    for _ in range(max(args.warmup, 3)):
+        out, wav = step_device()
+    torch.cuda.synchronize()
+    frames_local = out[9].sum().to(torch.int64).reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(frames_local, op=dist.ReduceOp.SUM)
+    frames_step = int(frames_local.item())                       # all ranks, one step
+    samples_step = frames_step * HOP
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches, _ = timed(step_device, args.steps)
+    clocks = sampler.stop() if sampler else None
+    value = samples_step * args.steps / (ms_total * 1e-3)
+
+    ms_mel, _, _ = timed(step_mel_only, args.steps)
+    mel_fps = frames_step * args.steps / (ms_mel * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    e2e_value = samples_step * args.steps / (ms_e2e * 1e-3)
+    h2d = spk_h.numel() * 8 + texts_h.numel() * 8 + lens_h.numel() * 8
+    d2h = int(wav.numel() * 4 + out[9].numel() * 8)
+
+    # ---- roofline of the dominant kernel class (conv1d implicit GEMM): one extra, untimed step with per-launch CUDA events
+    roof = None
+    if rank == 0:
+        lib.fs2_profile_begin()
+        step_device()
+        torch.cuda.synchronize()
+        ms = (C.c_double * 4)(); fl = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
+        lib.fs2_profile_end(ms, fl, cnt)
+        pk = peaks()
+        achieved = fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roof = {"kernel": "conv1d implicit-GEMM (all launches of one step: FFT-block projections / conv-FFN, predictors, PostNet, HiFi-GAN convs)",
+                "bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops_sustained"], "peak_source": pk["source"] + ", bf16 sustained (kernel timed inside a long step)",
+                "traffic": traffic, "launches_per_step": int(cnt[0]), "avg_launch_ms": ms[0] / max(int(cnt[0]), 1),
+                "share_of_step": ms[0] / max(sum(ms), 1e-9),
+                "other_classes_ms": {"attention": ms[1], "layernorm": ms[2], "other": ms[3]},
+                "algorithmic_tflop_per_step": fl[0] / 1e12}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n = max(1, min(args.cpu_sample, args.batch))
+            sps, fps, sec, cores, frames = cpu_reference_run(args, n, 1, 1)
+            cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"{n} of the {args.batch} utterances ({frames} mel frames), 1 warm-up + 1 timed pass ({sec:.1f} s), oracle port of "
+                             "the reference (same ATen CPU kernels), fp32, all host threads",
+                   "mel_frames_per_s_fastspeech2_only": fps}
+        line = {"metric": "audio_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world, frames_step / (args.batch * world)),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches,
+                "roofline": roof, "cpu_baseline": cpu,
+                "extra": {"mel_frames_per_s": frames_step * args.steps / (ms_total * 1e-3),
+                          "fastspeech2_only_mel_frames_per_s": mel_fps, "fastspeech2_only_ms_per_step": ms_mel / args.steps,
+                          "algorithmic_tflop_per_step": (FS2_FLOPS(args.phonemes, frames_step / (args.batch * world)) * args.batch * world
+                                                         + HIFIGAN_FLOPS_PER_FRAME * frames_step) / 1e12,
+                          "build": lib.fs2_build_info().decode()}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "RANK" not in os.environ:
+        port = 29000 + os.getpid() % 1000
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,221 @@
+// fp32 CUDA-core implicit-GEMM Conv1d over channels-last activations.
+//
+// This is the exact-precision path (plain fp32 FMA, fp32 accumulate): it serves every layer upstream of the
+// discrete duration / pitch-bucket decisions, where the parity budget is ~1e-6 (hard part 2),
+// and is the fallback for shapes the tcgen05 path does not take.  One kernel covers nn.Linear (taps = 1),
+// nn.Conv1d with dilation, and a phase group of ConvTranspose1d (see fs2b200.h).
+//
+// Tiling: CTA = 128 rows (time) x BN output channels, BK = 16, 256 threads, 8 x TN register tile per thread,
+// A tile transposed into smem so the inner product reads two broadcast float4 (A) and two conflict-free float4 (B)
+// per 64 FMAs; global->register->smem double buffering, one __syncthreads per k-step.
+#include "common.cuh"
+
+namespace fs2 {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int AS_LD = BM + 4;
+
+struct ConvP {
+  const float* x; long long xbs, xrs;
+  int B, T, Cin;
+  const float* w; const float* bias;
+  int N, taps, dil, pad;
+  int in_act; float in_slope;
+  int out_act; float out_slope;
+  const float* res; long long rbs, rrs;
+  float alpha; int accumulate;
+  const int* row_lens;
+  float* y; long long ybs, yrs;
+  int tiles_per_batch;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
+  constexpr int TN = BN / 16;              // 8, 4 or 2 columns per thread
+  constexpr int NG = (TN == 8) ? 2 : 1;    // column groups per thread
+  constexpr int GW = (TN == 2) ? 2 : 4;    // group width
+  constexpr int B_F4 = BK * BN / 4;        // float4 per B tile
+  constexpr int B_PER_THREAD = (B_F4 + 255) / 256;
+
+  __shared__ __align__(16) float As[2][BK][AS_LD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.x / p.tiles_per_batch;
+  const int t0 = (blockIdx.x % p.tiles_per_batch) * BM;
+  const int n0 = blockIdx.y * BN;
+
+  const float* xb = p.x + (long long)b * p.xbs;
+  const int kc = p.Cin / BK;               // k-steps per tap
+  const int KT = p.taps * kc;
+
+  float acc[8][NG * GW];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < NG * GW; j++) acc[i][j] = 0.f;
+
+  float4 ra[2];
+  float4 rb[B_PER_THREAD];
+
+  auto load_global = [&](int kt) {
+    const int tap = kt / kc;
+    const int c0 = (kt - tap * kc) * BK;
+    const int shift = tap * p.dil - p.pad;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int f = tid + i * 256;
+      const int row = f >> 2, c4 = f & 3;
+      const int t = t0 + row + shift;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t >= 0 && t < p.T) {
+        v = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * p.xrs + c0 + c4 * 4));
+        if (p.in_act == FS2_ACT_LRELU) {
+          v.x = v.x > 0.f ? v.x : v.x * p.in_slope;
+          v.y = v.y > 0.f ? v.y : v.y * p.in_slope;
+          v.z = v.z > 0.f ? v.z : v.z * p.in_slope;
+          v.w = v.w > 0.f ? v.w : v.w * p.in_slope;
+        }
+      }
+      ra[i] = v;
+    }
+    const float* wt = p.w + ((long long)tap * p.Cin + c0) * p.N;
+#pragma unroll
+    for (int i = 0; i < B_PER_THREAD; i++) {
+      const int f = tid + i * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < B_F4) {
+        const int k = f / (BN / 4), n4 = f % (BN / 4);
+        const int n = n0 + n4 * 4;
+        if (n < p.N) v = __ldg(reinterpret_cast<const float4*>(wt + (long long)k * p.N + n));
+      }
+      rb[i] = v;
+    }
+  };
+  auto store_smem = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int f = tid + i * 256;
+      const int row = f >> 2, c4 = f & 3;
+      As[buf][c4 * 4 + 0][row] = ra[i].x;
+      As[buf][c4 * 4 + 1][row] = ra[i].y;
+      As[buf][c4 * 4 + 2][row] = ra[i].z;
+      As[buf][c4 * 4 + 3][row] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER_THREAD; i++) {
+      const int f = tid + i * 256;
+      if (f < B_F4) {
+        const int k = f / (BN / 4), n4 = f % (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[buf][k][n4 * 4]) = rb[i];
+      }
+    }
+  };
+
+  load_global(0);
+  store_smem(0);
+  __syncthreads();
+
+  for (int kt = 0; kt < KT; kt++) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) load_global(kt + 1);
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[NG * GW];
+      if constexpr (TN == 2) {
+        const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
+        bv[0] = b0.x; bv[1] = b0.y;
+      } else {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+        if constexpr (TN == 8) {
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][BN / 2 + tx * 4]);
+          bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < NG * GW; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) store_smem(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias, activation, residual, alpha/accumulate, row mask ----
+  const int len_b = p.row_lens ? p.row_lens[b] : p.T;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int m = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
+    const int t = t0 + m;
+    if (t >= p.T) continue;
+    float* yrow = p.y + (long long)b * p.ybs + (long long)t * p.yrs;
+    const float* rrow = p.res ? (p.res + (long long)b * p.rbs + (long long)t * p.rrs) : nullptr;
+    const bool dead = t >= len_b;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      const int nb = n0 + ((TN == 2) ? tx * 2 : (g * (BN / 2) + tx * 4));
+      if (nb >= p.N) continue;
+      float v[GW];
+#pragma unroll
+      for (int j = 0; j < GW; j++) {
+        float u = acc[i][g * GW + j] + (p.bias ? __ldg(p.bias + nb + j) : 0.f);
+        u = apply_act(u, p.out_act, p.out_slope);
+        if (rrow) u += rrow[nb + j];
+        u *= p.alpha;
+        if (p.accumulate) u += yrow[nb + j];
+        v[j] = dead ? 0.f : u;
+      }
+      if constexpr (GW == 4) {
+        *reinterpret_cast<float4*>(yrow + nb) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        *reinterpret_cast<float2*>(yrow + nb) = make_float2(v[0], v[1]);
+      }
+    }
+  }
+}
+
+int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s) {
+  if (!a || !a->x || !a->w || !a->y) return FS2_ERR_ARG;
+  if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
+  if (a->Cin % BK != 0 || a->N % 4 != 0) return FS2_ERR_UNSUPPORTED;
+  if ((a->x_row_stride & 3) || (a->x_batch_stride & 3) || (a->y_row_stride & 3) || (a->y_batch_stride & 3)) return FS2_ERR_UNSUPPORTED;
+  if (a->res && ((a->res_row_stride & 3) || (a->res_batch_stride & 3))) return FS2_ERR_UNSUPPORTED;
+  if (!aligned16(a->x) || !aligned16(a->w) || !aligned16(a->y) || (a->res && !aligned16(a->res))) return FS2_ERR_ARG;
+  if (a->in_act != FS2_ACT_NONE && a->in_act != FS2_ACT_LRELU) return FS2_ERR_UNSUPPORTED;
+  ConvP p;
+  p.x = a->x; p.xbs = a->x_batch_stride; p.xrs = a->x_row_stride;
+  p.B = a->B; p.T = a->T; p.Cin = a->Cin;
+  p.w = a->w; p.bias = a->bias;
+  p.N = a->N; p.taps = a->taps; p.dil = a->dilation; p.pad = a->pad_left;
+  p.in_act = a->in_act; p.in_slope = a->in_slope;
+  p.out_act = a->out_act; p.out_slope = a->out_slope;
+  p.res = a->res; p.rbs = a->res_batch_stride; p.rrs = a->res_row_stride;
+  p.alpha = a->alpha; p.accumulate = a->accumulate;
+  p.row_lens = a->row_lens;
+  p.y = a->y; p.ybs = a->y_batch_stride; p.yrs = a->y_row_stride;
+  p.tiles_per_batch = (a->T + BM - 1) / BM;
+  const long long gx = (long long)p.tiles_per_batch * a->B;
+  if (gx > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
+  prof_before(s);
+  if (a->N > 64) {
+    dim3 grid((unsigned)gx, (a->N + 127) / 128);
+    conv_simt_kernel<128><<<grid, 256, 0, s>>>(p);
+  } else if (a->N > 32) {
+    dim3 grid((unsigned)gx, 1);
+    conv_simt_kernel<64><<<grid, 256, 0, s>>>(p);
+  } else {
+    dim3 grid((unsigned)gx, 1);
+    conv_simt_kernel<32><<<grid, 256, 0, s>>>(p);
+  }
+  prof_after(s, 0, 2.0 * a->B * a->T * (double)a->Cin * a->taps * a->N);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+}  // namespace fs2

@@ -1,0 +1,381 @@
+// Host-side orchestration of the two forward passes and the extern "C" surface declared in include/fs2b200.h.
+// No allocation, no synchronisation: every launch goes to the caller's stream, temporaries come from the caller's workspace.
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace fs2 {
+
+unsigned long long g_launch_count = 0;
+
+// ------------------------------------------------------------------ per-launch profiling (off unless armed)
+bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_pending;
+void prof_before(cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEventCreate(&g_prof_pending);
+  cudaEventRecord(g_prof_pending, s);
+}
+void prof_after(cudaStream_t s, int cls, double flops) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.a = g_prof_pending; r.cls = cls; r.flops = flops;
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.b, s);
+  g_prof.push_back(r);
+}
+
+// kernels / launchers defined in the other translation units
+int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s);
+int attention_simt(const fs2_attention_args* a, cudaStream_t s);
+int embed_positions(const fs2_embed_args* a, cudaStream_t s);
+int add_speaker(const fs2_rowbias_args* a, cudaStream_t s);
+int layernorm(const fs2_layernorm_args* a, cudaStream_t s);
+int variance_head(const fs2_variance_head_args* a, cudaStream_t s);
+int durations(const fs2_durations_args* a, cudaStream_t s);
+int length_regulate(const fs2_length_regulate_args* a, cudaStream_t s);
+int conv_post(const fs2_conv_post_args* a, cudaStream_t s);
+int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t s);
+
+// ------------------------------------------------------------------ workspace bump allocator
+struct Arena {
+  char* base; size_t cap, off;
+  bool dry;  // dry run: only measure
+  explicit Arena(void* p, size_t n) : base((char*)p), cap(n), off(0), dry(p == nullptr) {}
+  float* f32(size_t n) { return (float*)take(n * sizeof(float)); }
+  void* take(size_t bytes) {
+    const size_t a = (off + 255) & ~(size_t)255;
+    off = a + bytes;
+    if (dry) return (void*)(uintptr_t)256;  // non-null dummy
+    if (off > cap) return nullptr;
+    return base + a;
+  }
+};
+
+// contiguous [B][T][C] convolution helper
+static int conv(cudaStream_t s, const float* x, int B, int T, int Cin, const float* w, const float* bias, int N, int taps,
+                int dil, int pad, int out_act, float out_slope, float* y, const float* res = nullptr, int in_act = FS2_ACT_NONE,
+                float in_slope = 0.f, float alpha = 1.f, int accumulate = 0, const int32_t* row_lens = nullptr) {
+  fs2_conv1d_args a{};
+  a.x = x; a.x_batch_stride = (int64_t)T * Cin; a.x_row_stride = Cin;
+  a.B = B; a.T = T; a.Cin = Cin;
+  a.w = w; a.bias = bias; a.N = N; a.taps = taps; a.dilation = dil; a.pad_left = pad;
+  a.in_act = in_act; a.in_slope = in_slope; a.out_act = out_act; a.out_slope = out_slope;
+  a.res = res; a.res_batch_stride = (int64_t)T * N; a.res_row_stride = N;
+  a.alpha = alpha; a.accumulate = accumulate; a.row_lens = row_lens;
+  a.y = y; a.y_batch_stride = (int64_t)T * N; a.y_row_stride = N;
+  return conv1d_simt(&a, s);
+}
+
+static int ln(cudaStream_t s, const float* x, float* y, int B, int T, int C, const float* g, const float* b, const int32_t* lens) {
+  fs2_layernorm_args a{x, y, B, T, C, g, b, 1e-5f, lens};
+  return layernorm(&a, s);
+}
+
+struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; };
+
+// One FFT block in place on bufs.x  (transformer/Layers.py:21-30)
+static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_block_weights& w, const FftBufs& f, int B, int T,
+                     const int32_t* lens) {
+  const int D = m->d_model, F = m->d_inner;
+  FS2_TRY(conv(s, f.x, B, T, D, w.w_qkv, w.b_qkv, 3 * D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.qkv));
+  fs2_attention_args at{f.qkv, f.ctx, B, T, m->n_head, D / m->n_head, lens, 1.0f / sqrtf((float)(D / m->n_head))};
+  FS2_TRY(attention_simt(&at, s));
+  FS2_TRY(conv(s, f.ctx, B, T, D, w.w_o, w.b_o, D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.tmp, f.x));
+  FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln1_g, w.ln1_b, lens));
+  FS2_TRY(conv(s, f.x, B, T, D, w.w_1, w.b_1, F, m->k1, 1, (m->k1 - 1) / 2, FS2_ACT_RELU, 0.f, f.hid));
+  FS2_TRY(conv(s, f.hid, B, T, F, w.w_2, w.b_2, D, m->k2, 1, (m->k2 - 1) / 2, FS2_ACT_NONE, 0.f, f.tmp, f.x));
+  FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln2_g, w.ln2_b, lens));
+  return FS2_OK;
+}
+
+static bool model_ok(const fs2_acoustic_model* m) {
+  return m && m->d_model > 0 && m->n_head > 0 && m->d_model % m->n_head == 0 && m->n_enc >= 0 && m->n_enc <= FS2_MAX_LAYERS &&
+         m->n_dec >= 0 && m->n_dec <= FS2_MAX_LAYERS && m->n_postnet >= 0 && m->n_postnet <= FS2_MAX_POSTNET && m->d_inner > 0 &&
+         m->n_mel > 0 && m->vp_filter > 0;
+}
+
+static FftBufs fft_bufs(Arena& ar, const fs2_acoustic_model* m, size_t rows) {
+  FftBufs f;
+  f.x = ar.f32(rows * m->d_model);
+  f.tmp = ar.f32(rows * m->d_model);
+  f.qkv = ar.f32(rows * 3 * m->d_model);
+  f.ctx = ar.f32(rows * m->d_model);
+  f.hid = ar.f32(rows * m->d_inner);
+  return f;
+}
+
+// ------------------------------------------------------------------ phase 1
+static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cudaStream_t s, Arena& ar) {
+  const int B = a->B, L = a->L, D = m->d_model, VF = m->vp_filter;
+  const size_t rows = (size_t)B * L;
+  FftBufs f = fft_bufs(ar, m, rows);
+  float* h1 = ar.f32(rows * VF);
+  float* h2 = ar.f32(rows * VF);
+  if (ar.dry) return FS2_OK;
+  if (!f.x || !f.tmp || !f.qkv || !f.ctx || !f.hid || !h1 || !h2) return FS2_ERR_WORKSPACE;
+  if (L > m->enc_pos_rows) return FS2_ERR_ARG;
+
+  fs2_embed_args e{a->texts, m->word_emb, m->enc_pos, f.x, B, L, D, m->n_vocab};
+  FS2_TRY(embed_positions(&e, s));
+  for (int i = 0; i < m->n_enc; i++) FS2_TRY(fft_block(s, m, m->enc[i], f, B, L, a->src_lens));
+  if (m->spk_emb) {
+    if (!a->speakers) return FS2_ERR_ARG;
+    fs2_rowbias_args r{f.x, m->spk_emb, a->speakers, B, L, D, m->n_speakers};
+    FS2_TRY(add_speaker(&r, s));
+  }
+  // x_adapted starts as the encoder output; pitch / energy embeddings are added in place (modules.py:117-126)
+  cudaError_t ce = cudaMemcpyAsync(a->x_adapted, f.x, rows * D * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (ce != cudaSuccess) return FS2_ERR_CUDA - (int)ce;
+
+  auto predictor = [&](const fs2_predictor_weights& w, const float* x, float control, const float* target, const float* bins,
+                       const float* emb, float* pred_out) -> int {
+    const int k = m->vp_kernel;
+    FS2_TRY(conv(s, x, B, L, D, w.w_c1, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
+    FS2_TRY(ln(s, h1, h2, B, L, VF, w.ln1_g, w.ln1_b, nullptr));
+    FS2_TRY(conv(s, h2, B, L, VF, w.w_c2, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
+    FS2_TRY(ln(s, h1, h2, B, L, VF, w.ln2_g, w.ln2_b, nullptr));
+    fs2_variance_head_args v{};
+    v.h = h2; v.w = w.w_out; v.b = w.b_out; v.B = B; v.L = L; v.C = VF;
+    v.lens = a->src_lens; v.control = control; v.target = target;
+    v.bins = bins; v.n_edges = m->n_bins - 1; v.emb = emb; v.D = D; v.x = a->x_adapted; v.pred_out = pred_out;
+    return variance_head(&v, s);
+  };
+  // duration on the un-embedded x; pitch on x; energy on x + pitch embedding.  energy uses p_control (modules.py:124).
+  FS2_TRY(predictor(m->dur, a->x_adapted, 1.f, nullptr, nullptr, nullptr, a->logd_pred));
+  FS2_TRY(predictor(m->pitch, a->x_adapted, a->p_control, a->p_target, m->pitch_bins, m->pitch_emb, a->p_pred));
+  FS2_TRY(predictor(m->energy, a->x_adapted, a->p_control, a->e_target, m->energy_bins, m->energy_emb, a->e_pred));
+
+  fs2_durations_args d{};
+  d.src = a->d_target ? a->d_target : a->logd_pred; d.use_target = a->d_target != nullptr; d.d_control = a->d_control;
+  d.B = B; d.L = L; d.d_rounded = a->d_target ? nullptr : a->d_rounded; d.cum = a->cum_dur; d.mel_lens = a->mel_lens;
+  d.mel_lens32 = a->mel_lens32; d.len_stats = a->len_stats;
+  FS2_TRY(durations(&d, s));
+  if (a->len_stats_host) {
+    ce = cudaMemcpyAsync(a->len_stats_host, a->len_stats, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    if (ce != cudaSuccess) return FS2_ERR_CUDA - (int)ce;
+  }
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ phase 2
+static int decode_impl(const fs2_acoustic_model* m, const fs2_decode_args* a, cudaStream_t s, Arena& ar) {
+  const int B = a->B, T = a->T, D = m->d_model;
+  const size_t rows = (size_t)B * T;
+  FftBufs f = fft_bufs(ar, m, rows);
+  int pc = 0;
+  for (int i = 0; i < m->n_postnet; i++) pc = pc > m->post_cout[i] ? pc : m->post_cout[i];
+  float* pa = ar.f32(rows * pc);
+  float* pb = ar.f32(rows * pc);
+  if (ar.dry) return FS2_OK;
+  if (!f.x || !f.tmp || !f.qkv || !f.ctx || !f.hid || !pa || !pb) return FS2_ERR_WORKSPACE;
+  if (T > m->dec_pos_rows) return FS2_ERR_ARG;
+
+  fs2_length_regulate_args lr{a->x_adapted, a->cum_dur, m->dec_pos, f.x, B, a->L, T, D};
+  FS2_TRY(length_regulate(&lr, s));
+  for (int i = 0; i < m->n_dec; i++) FS2_TRY(fft_block(s, m, m->dec[i], f, B, T, a->mel_mask_lens));
+  FS2_TRY(conv(s, f.x, B, T, D, m->w_mel, m->b_mel, m->n_mel, 1, 1, 0, FS2_ACT_NONE, 0.f, a->mel));
+  // PostNet: eval BatchNorm folded into (w, b) by the packer; unmasked, tanh on all but the last (Layers.py:129-137)
+  const float* cur = a->mel;
+  for (int i = 0; i < m->n_postnet; i++) {
+    const bool last = i == m->n_postnet - 1;
+    float* dst = last ? a->postnet_mel : ((i & 1) ? pb : pa);
+    FS2_TRY(conv(s, cur, B, T, m->post_cin[i], m->w_post[i], m->b_post[i], m->post_cout[i], m->post_k, 1, (m->post_k - 1) / 2,
+                 last ? FS2_ACT_NONE : FS2_ACT_TANH, 0.f, dst, last ? a->mel : nullptr));
+    cur = dst;
+  }
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ vocoder
+static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, cudaStream_t s, Arena& ar) {
+  const int B = a->B, T = a->T;
+  size_t per_frame = (size_t)m->c0;  // floats per mel frame of the widest activation
+  {
+    int up = 1, ch = m->c0;
+    for (int i = 0; i < m->n_stages; i++) {
+      up *= m->rates[i];
+      ch /= 2;
+      per_frame = per_frame > (size_t)up * ch ? per_frame : (size_t)up * ch;
+    }
+  }
+  const size_t n = (size_t)B * T * per_frame;
+  float* bx = ar.f32(n);
+  float* bu = ar.f32(n);
+  float* bt = ar.f32(n);
+  float* r1 = ar.f32(n);
+  float* r2 = ar.f32(n);
+  if (ar.dry) return FS2_OK;
+  if (!bx || !bu || !bt || !r1 || !r2) return FS2_ERR_WORKSPACE;
+
+  {  // conv_pre reads the (possibly strided) channels-last mel view
+    fs2_conv1d_args c{};
+    c.x = a->mel; c.x_batch_stride = a->mel_batch_stride; c.x_row_stride = a->mel_row_stride;
+    c.B = B; c.T = T; c.Cin = m->n_mel; c.w = m->w_pre; c.bias = m->b_pre; c.N = m->c0; c.taps = 7; c.dilation = 1; c.pad_left = 3;
+    c.alpha = 1.f; c.y = bx; c.y_batch_stride = (int64_t)T * m->c0; c.y_row_stride = m->c0;
+    FS2_TRY(conv1d_simt(&c, s));
+  }
+  int Ti = T, C = m->c0;
+  const float inv_nk = 1.f / (float)m->n_kernels;
+  for (int i = 0; i < m->n_stages; i++) {
+    const int u = m->rates[i], Co = C / 2;
+    if (m->up_k[i] != 2 * u || (u & 1)) return FS2_ERR_UNSUPPORTED;
+    // ---- lrelu + ConvTranspose1d as two 2-tap phase-group convolutions (hifigan/models.py:152-153)
+    for (int g = 0; g < 2; g++) {
+      fs2_conv1d_args c{};
+      c.x = bx; c.x_batch_stride = (int64_t)Ti * C; c.x_row_stride = C; c.B = B; c.T = Ti; c.Cin = C;
+      c.w = g == 0 ? m->w_up_a[i] : m->w_up_b[i];
+      c.bias = m->b_up[i] + (size_t)g * (u / 2) * Co;
+      c.N = (u / 2) * Co; c.taps = 2; c.dilation = 1; c.pad_left = g == 0 ? 1 : 0;
+      c.in_act = FS2_ACT_LRELU; c.in_slope = 0.1f; c.alpha = 1.f;
+      c.y = bu + (size_t)g * (u / 2) * Co; c.y_batch_stride = (int64_t)Ti * u * Co; c.y_row_stride = (int64_t)u * Co;
+      FS2_TRY(conv1d_simt(&c, s));
+    }
+    Ti *= u; C = Co;
+    // ---- mean of the multi-receptive-field ResBlocks (models.py:154-160, ResBlock.forward :96-103)
+    for (int j = 0; j < m->n_kernels; j++) {
+      const int rb = i * m->n_kernels + j, k = m->rb_k[j];
+      const float* r = bu;
+      for (int d = 0; d < m->n_dil; d++) {
+        const int dil = m->rb_dil[j][d];
+        FS2_TRY(conv(s, r, B, Ti, C, m->w_rb1[rb][d], m->b_rb1[rb][d], C, k, dil, (k * dil - dil) / 2, FS2_ACT_LRELU, 0.1f, bt, nullptr,
+                     FS2_ACT_LRELU, 0.1f));
+        const bool last = d == m->n_dil - 1;
+        float* dst = last ? bx : (r == r1 ? r2 : r1);
+        FS2_TRY(conv(s, bt, B, Ti, C, m->w_rb2[rb][d], m->b_rb2[rb][d], C, k, 1, (k - 1) / 2, FS2_ACT_NONE, 0.f, dst, r, FS2_ACT_NONE,
+                     0.f, last ? inv_nk : 1.f, last && j > 0));
+        r = dst;
+      }
+    }
+  }
+  fs2_conv_post_args p{bx, B, Ti, C, m->w_post, m->b_post, 7, 0.01f, a->wav};
+  return conv_post(&p, s);
+}
+
+}  // namespace fs2
+
+// ====================================================================== extern "C"
+using namespace fs2;
+#define S(x) ((cudaStream_t)(x))
+
+extern "C" {
+
+int fs2_abi_version(void) { return 1; }
+int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count; }
+size_t fs2_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(fs2_conv1d_args);
+    case 1: return sizeof(fs2_layernorm_args);
+    case 2: return sizeof(fs2_attention_args);
+    case 3: return sizeof(fs2_embed_args);
+    case 4: return sizeof(fs2_rowbias_args);
+    case 5: return sizeof(fs2_variance_head_args);
+    case 6: return sizeof(fs2_durations_args);
+    case 7: return sizeof(fs2_length_regulate_args);
+    case 8: return sizeof(fs2_conv_post_args);
+    case 9: return sizeof(fs2_acoustic_model);
+    case 10: return sizeof(fs2_encode_args);
+    case 11: return sizeof(fs2_decode_args);
+    case 12: return sizeof(fs2_vocoder_model);
+    case 13: return sizeof(fs2_vocoder_args);
+    default: return 0;
+  }
+}
+int fs2_profile_begin(void) {
+  g_prof.clear();
+  g_prof_on = true;
+  return FS2_OK;
+}
+int fs2_profile_end(double* ms, double* flops, int64_t* launches) {
+  g_prof_on = false;
+  if (!ms || !flops || !launches) return FS2_ERR_ARG;
+  for (int i = 0; i < FS2_PROF_CLASSES; i++) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  int rc = FS2_OK;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) rc = FS2_ERR_CUDA - (int)e;
+    const int c = (r.cls >= 0 && r.cls < FS2_PROF_CLASSES) ? r.cls : FS2_PROF_CLASSES - 1;
+    ms[c] += t; flops[c] += r.flops; launches[c] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return rc;
+}
+const char* fs2_build_info(void) { return "fs2b200 sm_100a fp32-simt path, built " __DATE__ " " __TIME__; }
+
+int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t st) { return conv1d_simt(a, S(st)); }
+int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t st) { return layernorm(a, S(st)); }
+int fs2_attention(const fs2_attention_args* a, fs2_stream_t st) { return attention_simt(a, S(st)); }
+int fs2_embed_positions(const fs2_embed_args* a, fs2_stream_t st) { return embed_positions(a, S(st)); }
+int fs2_add_speaker(const fs2_rowbias_args* a, fs2_stream_t st) { return add_speaker(a, S(st)); }
+int fs2_variance_head(const fs2_variance_head_args* a, fs2_stream_t st) { return variance_head(a, S(st)); }
+int fs2_durations(const fs2_durations_args* a, fs2_stream_t st) { return durations(a, S(st)); }
+int fs2_length_regulate(const fs2_length_regulate_args* a, fs2_stream_t st) { return length_regulate(a, S(st)); }
+int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t st) { return conv_post(a, S(st)); }
+int fs2_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, fs2_stream_t st) {
+  return transpose_bct_to_btc(in, out, B, C, T, S(st));
+}
+
+size_t fs2_encode_workspace_bytes(const fs2_acoustic_model* m, int B, int L) {
+  if (!model_ok(m) || B <= 0 || L <= 0) return 0;
+  Arena ar(nullptr, 0);
+  fs2_encode_args a{};
+  a.B = B; a.L = L;
+  encode_impl(m, &a, nullptr, ar);
+  return ar.off + 256;
+}
+
+int fs2_acoustic_encode(const fs2_acoustic_model* m, const fs2_encode_args* a, fs2_stream_t st) {
+  if (!model_ok(m) || !a || a->B <= 0 || a->L <= 0) return FS2_ERR_ARG;
+  if (!a->texts || !a->src_lens || !a->p_pred || !a->e_pred || !a->logd_pred || !a->mel_lens || !a->cum_dur || !a->x_adapted ||
+      !a->len_stats || !a->workspace)
+    return FS2_ERR_ARG;
+  if (!a->d_target && !a->d_rounded) return FS2_ERR_ARG;
+  if (m->d_model / m->n_head != 128) return FS2_ERR_UNSUPPORTED;
+  Arena ar(a->workspace, a->workspace_bytes);
+  return encode_impl(m, a, S(st), ar);
+}
+
+size_t fs2_decode_workspace_bytes(const fs2_acoustic_model* m, int B, int T) {
+  if (!model_ok(m) || B <= 0 || T <= 0) return 0;
+  Arena ar(nullptr, 0);
+  fs2_decode_args a{};
+  a.B = B; a.T = T;
+  decode_impl(m, &a, nullptr, ar);
+  return ar.off + 256;
+}
+
+int fs2_acoustic_decode(const fs2_acoustic_model* m, const fs2_decode_args* a, fs2_stream_t st) {
+  if (!model_ok(m) || !a || a->B <= 0 || a->L <= 0 || a->T <= 0) return FS2_ERR_ARG;
+  if (!a->x_adapted || !a->cum_dur || !a->mel_mask_lens || !a->mel || !a->postnet_mel || !a->workspace) return FS2_ERR_ARG;
+  if (m->d_model / m->n_head != 128) return FS2_ERR_UNSUPPORTED;
+  Arena ar(a->workspace, a->workspace_bytes);
+  return decode_impl(m, a, S(st), ar);
+}
+
+static bool vocoder_ok(const fs2_vocoder_model* m) {
+  return m && m->n_stages > 0 && m->n_stages <= FS2_MAX_STAGES && m->n_kernels > 0 && m->n_kernels * m->n_stages <= FS2_MAX_RESBLOCKS &&
+         m->n_dil > 0 && m->n_dil <= FS2_MAX_DIL && m->c0 > 0 && m->n_mel > 0;
+}
+
+size_t fs2_vocoder_workspace_bytes(const fs2_vocoder_model* m, int B, int T) {
+  if (!vocoder_ok(m) || B <= 0 || T <= 0) return 0;
+  Arena ar(nullptr, 0);
+  fs2_vocoder_args a{};
+  a.B = B; a.T = T;
+  vocoder_impl(m, &a, nullptr, ar);
+  return ar.off + 256;
+}
+
+int fs2_vocoder_forward(const fs2_vocoder_model* m, const fs2_vocoder_args* a, fs2_stream_t st) {
+  if (!vocoder_ok(m) || !a || a->B <= 0 || a->T <= 0 || !a->mel || !a->wav || !a->workspace) return FS2_ERR_ARG;
+  Arena ar(a->workspace, a->workspace_bytes);
+  return vocoder_impl(m, a, S(st), ar);
+}
+
+}  // extern "C"

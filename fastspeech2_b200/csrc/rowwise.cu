@@ -1,0 +1,362 @@
+// HBM-bound row kernels: embedding + positions, speaker add, LayerNorm + pad mask, variance head
+// (row dot + bucketize + embedding add), duration rounding + prefix sum, length-regulator gather,
+// conv_post + tanh, and the [B,C,T] -> [B,T,C] transpose.  All fp32, float4 I/O, one warp per row.
+#include "common.cuh"
+
+namespace fs2 {
+
+// ------------------------------------------------------------------ embedding + position (Models.py:89-91)
+__global__ void embed_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                             const float* __restrict__ pos, float* __restrict__ y, int B, int L, int D4, int n_vocab) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B * L) return;
+  const int lane = threadIdx.x & 31;
+  const int l = row % L;
+  long long id = ids[row];
+  if (id < 0 || id >= n_vocab) id = 0;  // the reference would raise; stay in bounds
+  const float4* e = reinterpret_cast<const float4*>(table) + id * D4;
+  const float4* p = reinterpret_cast<const float4*>(pos) + (long long)l * D4;
+  float4* o = reinterpret_cast<float4*>(y) + (long long)row * D4;
+  for (int c = lane; c < D4; c += 32) {
+    const float4 a = __ldg(e + c), q = __ldg(p + c);
+    o[c] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
+int embed_positions(const fs2_embed_args* a, cudaStream_t s) {
+  if (!a || !a->ids || !a->table || !a->pos || !a->y || a->B <= 0 || a->L <= 0 || a->D <= 0) return FS2_ERR_ARG;
+  if (a->D % 4) return FS2_ERR_UNSUPPORTED;
+  const int rows = a->B * a->L;
+  embed_kernel<<<(rows + 7) / 8, 256, 0, s>>>(reinterpret_cast<const long long*>(a->ids), a->table, a->pos, a->y, a->B, a->L,
+                                              a->D / 4, a->n_vocab);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ speaker add (fastspeech2.py:68-71)
+__global__ void rowbias_kernel(float* __restrict__ x, const float* __restrict__ table, const long long* __restrict__ idx, int B,
+                               int L, int D4, int n_rows) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B * L) return;
+  const int lane = threadIdx.x & 31;
+  long long id = idx[row / L];
+  if (id < 0 || id >= n_rows) id = 0;
+  const float4* e = reinterpret_cast<const float4*>(table) + id * D4;
+  float4* o = reinterpret_cast<float4*>(x) + (long long)row * D4;
+  for (int c = lane; c < D4; c += 32) {
+    const float4 a = __ldg(e + c);
+    float4 v = o[c];
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    o[c] = v;
+  }
+}
+
+int add_speaker(const fs2_rowbias_args* a, cudaStream_t s) {
+  if (!a || !a->x || !a->table || !a->idx || a->B <= 0 || a->L <= 0 || a->D <= 0) return FS2_ERR_ARG;
+  if (a->D % 4) return FS2_ERR_UNSUPPORTED;
+  const int rows = a->B * a->L;
+  rowbias_kernel<<<(rows + 7) / 8, 256, 0, s>>>(a->x, a->table, reinterpret_cast<const long long*>(a->idx), a->B, a->L, a->D / 4,
+                                                a->n_rows);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ LayerNorm + pad-row zeroing
+// One warp per row; the row lives in registers (C <= 1024), two-pass mean / variance like ATen's CPU kernel.
+__global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int T, int C4,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 const int* __restrict__ row_lens) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4* o = reinterpret_cast<float4*>(y) + (long long)row * C4;
+  if (row_lens) {
+    const int b = row / T, t = row - b * T;
+    if (t >= row_lens[b]) {
+      for (int c = lane; c < C4; c += 32) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+  }
+  const float4* in = reinterpret_cast<const float4*>(x) + (long long)row * C4;
+  float4 v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = lane + i * 32;
+    if (c < C4) {
+      v[i] = in[c];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float inv_c = 1.f / (float)(C4 * 4);
+  const float mean = warp_sum(sum) * inv_c;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = lane + i * 32;
+    if (c < C4) {
+      const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b2 * b2) + (c2 * c2 + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = lane + i * 32;
+    if (c < C4) {
+      const float4 g = __ldg(g4 + c), bb = __ldg(b4 + c);
+      o[c] = make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                         (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+    }
+  }
+}
+
+int layernorm(const fs2_layernorm_args* a, cudaStream_t s) {
+  if (!a || !a->x || !a->y || !a->gamma || !a->beta || a->B <= 0 || a->T <= 0 || a->C <= 0) return FS2_ERR_ARG;
+  if (a->C % 4 || a->C > 1024) return FS2_ERR_UNSUPPORTED;
+  const long long rows = (long long)a->B * a->T;
+  if (rows > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
+  prof_before(s);
+  layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a->x, a->y, (int)rows, a->T, a->C / 4, a->gamma, a->beta, a->eps,
+                                                             a->row_lens);
+  prof_after(s, 2, 0.0);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ variance head (modules.py:80-100, :246-250)
+__global__ void variance_head_kernel(const fs2_variance_head_args a) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.B * a.L) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / a.L, l = row - b * a.L;
+  const float4* h = reinterpret_cast<const float4*>(a.h) + (long long)row * (a.C / 4);
+  const float4* w = reinterpret_cast<const float4*>(a.w);
+  float acc = 0.f;
+  for (int c = lane; c < a.C / 4; c += 32) {
+    const float4 u = h[c], q = __ldg(w + c);
+    acc += (u.x * q.x + u.y * q.y) + (u.z * q.z + u.w * q.w);
+  }
+  float pred = warp_sum(acc) + __ldg(a.b);
+  if (a.lens && l >= a.lens[b]) pred = 0.f;  // masked_fill(mask, 0.0)
+  float key = pred;
+  if (a.bins) {
+    if (a.target) {
+      key = a.target[row];
+    } else {
+      pred = pred * a.control;
+      key = pred;
+    }
+  }
+  if (lane == 0) a.pred_out[row] = pred;
+  if (!a.bins) return;
+  // torch.bucketize(right=False): number of edges strictly below key
+  int lo = 0, hi = a.n_edges;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a.bins + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  const float4* e = reinterpret_cast<const float4*>(a.emb) + (long long)lo * (a.D / 4);
+  float4* x = reinterpret_cast<float4*>(a.x) + (long long)row * (a.D / 4);
+  for (int c = lane; c < a.D / 4; c += 32) {
+    const float4 q = __ldg(e + c);
+    float4 v = x[c];
+    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    x[c] = v;
+  }
+}
+
+int variance_head(const fs2_variance_head_args* a, cudaStream_t s) {
+  if (!a || !a->h || !a->w || !a->b || !a->pred_out || a->B <= 0 || a->L <= 0 || a->C <= 0) return FS2_ERR_ARG;
+  if (a->C % 4) return FS2_ERR_UNSUPPORTED;
+  if (a->bins && (!a->emb || !a->x || a->n_edges <= 0 || a->D <= 0 || a->D % 4)) return FS2_ERR_ARG;
+  const int rows = a->B * a->L;
+  variance_head_kernel<<<(rows + 7) / 8, 256, 0, s>>>(*a);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ durations (modules.py:132-135, :185-187)
+// One CTA per utterance: round-half-even (rintf == torch.round), truncate, block-wide inclusive scan.
+__global__ void durations_kernel(const fs2_durations_args a) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nw = blockDim.x >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < a.L; base += blockDim.x) {
+    const int l = base + tid;
+    int reps = 0;
+    if (l < a.L) {
+      const float s = a.src[(long long)b * a.L + l];
+      float d;
+      if (a.use_target) {
+        d = s;
+      } else {
+        d = fmaxf(rintf(expf(s) - 1.f) * a.d_control, 0.f);
+        if (a.d_rounded) a.d_rounded[(long long)b * a.L + l] = d;
+      }
+      reps = max((int)fminf(d, 1.0e6f), 0);  // int() truncation toward zero (bounded so a wild exp() cannot overflow int)
+    }
+    int v = reps;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    if (lane == 31) warp_tot[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      int t = lane < nw ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += n;
+      }
+      warp_tot[lane] = t;  // inclusive totals
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int prefix = carry + (wid ? warp_tot[wid - 1] : 0) + v;
+    if (l < a.L) a.cum[(long long)b * a.L + l] = prefix;
+    __syncthreads();
+    if (tid == 0) carry_s = carry + warp_tot[nw - 1];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int total = carry_s;
+    a.mel_lens[b] = total;
+    if (a.mel_lens32) a.mel_lens32[b] = total;
+    atomicMax(a.len_stats, total);
+    atomicAdd(a.len_stats + 1, total);
+  }
+}
+
+int durations(const fs2_durations_args* a, cudaStream_t s) {
+  if (!a || !a->src || !a->cum || !a->mel_lens || !a->len_stats || a->B <= 0 || a->L <= 0) return FS2_ERR_ARG;
+  cudaError_t e = cudaMemsetAsync(a->len_stats, 0, 2 * sizeof(int), s);
+  if (e != cudaSuccess) return FS2_ERR_CUDA - (int)e;
+  durations_kernel<<<a->B, 256, 0, s>>>(*a);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ length regulator gather (modules.py:167-194)
+// One warp per output frame: binary search of the inclusive duration prefix sums (L2/L1 resident, 4*L bytes per utterance),
+// then a coalesced float4 copy of the source phoneme row with the decoder position row added (Models.py:158-160).
+__global__ void length_regulate_kernel(const fs2_length_regulate_args a) {
+  const long long frame = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (frame >= (long long)a.B * a.T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(frame / a.T), t = (int)(frame - (long long)b * a.T);
+  const int* cum = a.cum + (long long)b * a.L;
+  const int total = __ldg(cum + a.L - 1);
+  const int D4 = a.D / 4;
+  float4* o = reinterpret_cast<float4*>(a.y) + frame * D4;
+  const float4* pos = a.pos ? reinterpret_cast<const float4*>(a.pos) + (long long)t * D4 : nullptr;
+  if (t >= total) {
+    for (int c = lane; c < D4; c += 32) o[c] = pos ? __ldg(pos + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  int lo = 0, hi = a.L - 1;  // first i with cum[i] > t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cum + mid) > t) hi = mid; else lo = mid + 1;
+  }
+  const float4* src = reinterpret_cast<const float4*>(a.x) + ((long long)b * a.L + lo) * D4;
+  for (int c = lane; c < D4; c += 32) {
+    float4 v = __ldg(src + c);
+    if (pos) {
+      const float4 q = __ldg(pos + c);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    o[c] = v;
+  }
+}
+
+int length_regulate(const fs2_length_regulate_args* a, cudaStream_t s) {
+  if (!a || !a->x || !a->cum || !a->y || a->B <= 0 || a->L <= 0 || a->T <= 0 || a->D <= 0) return FS2_ERR_ARG;
+  if (a->D % 4) return FS2_ERR_UNSUPPORTED;
+  const long long frames = (long long)a->B * a->T;
+  prof_before(s);
+  length_regulate_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, s>>>(*a);
+  prof_after(s, 3, 0.0);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ conv_post + tanh (hifigan/models.py:161-163)
+// C_in = 32, one output channel: 128 B per input row, HBM-bound.  One thread per output sample; neighbouring threads
+// share input rows through L1.
+__global__ void conv_post_kernel(const fs2_conv_post_args a) {
+  extern __shared__ float wsm[];  // [taps][C]
+  for (int i = threadIdx.x; i < a.taps * a.C; i += blockDim.x) wsm[i] = a.w[i];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.B * a.T) return;
+  const int b = (int)(idx / a.T), t = (int)(idx - (long long)b * a.T);
+  const int pad = (a.taps - 1) / 2;
+  const int C4 = a.C / 4;
+  float acc = __ldg(a.bias);
+  for (int j = 0; j < a.taps; j++) {
+    const int ti = t + j - pad;
+    if (ti < 0 || ti >= a.T) continue;
+    const float4* xr = reinterpret_cast<const float4*>(a.x) + ((long long)b * a.T + ti) * C4;
+    const float* wj = wsm + j * a.C;
+    for (int c = 0; c < C4; c++) {
+      float4 v = __ldg(xr + c);
+      v.x = v.x > 0.f ? v.x : v.x * a.in_slope;
+      v.y = v.y > 0.f ? v.y : v.y * a.in_slope;
+      v.z = v.z > 0.f ? v.z : v.z * a.in_slope;
+      v.w = v.w > 0.f ? v.w : v.w * a.in_slope;
+      acc = fmaf(v.x, wj[c * 4 + 0], acc);
+      acc = fmaf(v.y, wj[c * 4 + 1], acc);
+      acc = fmaf(v.z, wj[c * 4 + 2], acc);
+      acc = fmaf(v.w, wj[c * 4 + 3], acc);
+    }
+  }
+  a.wav[idx] = tanhf(acc);
+}
+
+int conv_post(const fs2_conv_post_args* a, cudaStream_t s) {
+  if (!a || !a->x || !a->w || !a->bias || !a->wav || a->B <= 0 || a->T <= 0 || a->C <= 0 || a->taps <= 0) return FS2_ERR_ARG;
+  if (a->C % 4 || a->taps * a->C * 4 > 32768) return FS2_ERR_UNSUPPORTED;
+  const long long n = (long long)a->B * a->T;
+  prof_before(s);
+  conv_post_kernel<<<(unsigned)((n + 255) / 256), 256, a->taps * a->C * sizeof(float), s>>>(*a);
+  prof_after(s, 3, 2.0 * n * a->taps * a->C);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+// ------------------------------------------------------------------ [B,C,T] -> [B,T,C]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* ib = in + (long long)b * C * T;
+  float* ob = out + (long long)b * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T) tile[i][threadIdx.x] = ib[(long long)c * T + t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (c < C && t < T) ob[(long long)t * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t s) {
+  if (!in || !out || B <= 0 || C <= 0 || T <= 0) return FS2_ERR_ARG;
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(in, out, C, T);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
+}  // namespace fs2

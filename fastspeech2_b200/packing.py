@@ -1,0 +1,134 @@
+"""Weight re-layout for the sm_100a kernels (pure tensor permutations, device-agnostic, run once per load).
+
+Inputs are reference-keyed tensors; outputs are the layouts include/fs2b200.h documents:
+conv / linear weights as [taps][C_in][C_out] (C_out contiguous), QKV concatenated, eval BatchNorm folded into the
+PostNet convs, weight-norm folded, ConvTranspose1d split into its two 2-tap phase groups.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def conv_w(w: Tensor) -> Tensor:
+    """nn.Conv1d weight [C_out, C_in, k] -> [k][C_in][C_out]."""
+    return w.permute(2, 1, 0).contiguous()
+
+
+def lin_w(w: Tensor) -> Tensor:
+    """nn.Linear weight [out, in] -> [in][out]."""
+    return w.t().contiguous()
+
+
+def pack_fft_block(g: Callable[[str], Tensor], pfx: str) -> Dict[str, Tensor]:
+    a, f = pfx + ".slf_attn.", pfx + ".pos_ffn."
+    return {
+        "w_qkv": torch.cat([lin_w(g(a + "w_qs.weight")), lin_w(g(a + "w_ks.weight")), lin_w(g(a + "w_vs.weight"))], dim=1).contiguous(),
+        "b_qkv": torch.cat([g(a + "w_qs.bias"), g(a + "w_ks.bias"), g(a + "w_vs.bias")]).contiguous(),
+        "w_o": lin_w(g(a + "fc.weight")), "b_o": g(a + "fc.bias").contiguous(),
+        "ln1_g": g(a + "layer_norm.weight").contiguous(), "ln1_b": g(a + "layer_norm.bias").contiguous(),
+        "w_1": conv_w(g(f + "w_1.weight")), "b_1": g(f + "w_1.bias").contiguous(),
+        "w_2": conv_w(g(f + "w_2.weight")), "b_2": g(f + "w_2.bias").contiguous(),
+        "ln2_g": g(f + "layer_norm.weight").contiguous(), "ln2_b": g(f + "layer_norm.bias").contiguous(),
+    }
+
+
+def pack_predictor(g: Callable[[str], Tensor], pfx: str) -> Dict[str, Tensor]:
+    c = pfx + ".conv_layer."
+    return {
+        "w_c1": conv_w(g(c + "conv1d_1.conv.weight")), "b_c1": g(c + "conv1d_1.conv.bias").contiguous(),
+        "ln1_g": g(c + "layer_norm_1.weight").contiguous(), "ln1_b": g(c + "layer_norm_1.bias").contiguous(),
+        "w_c2": conv_w(g(c + "conv1d_2.conv.weight")), "b_c2": g(c + "conv1d_2.conv.bias").contiguous(),
+        "ln2_g": g(c + "layer_norm_2.weight").contiguous(), "ln2_b": g(c + "layer_norm_2.bias").contiguous(),
+        "w_out": g(pfx + ".linear_layer.weight")[0].contiguous(), "b_out": g(pfx + ".linear_layer.bias").contiguous(),
+    }
+
+
+def fold_batchnorm(w: Tensor, b: Tensor, gamma: Tensor, beta: Tensor, mean: Tensor, var: Tensor, eps: float = 1e-5):
+    """Conv1d followed by eval-mode BatchNorm1d == one conv (transformer/Layers.py:94,110,125).  fp64 fold, rounded once."""
+    scale = gamma.double() / torch.sqrt(var.double() + eps)
+    wf = (w.double() * scale[:, None, None]).float()
+    bf = ((b.double() - mean.double()) * scale + beta.double()).float()
+    return wf, bf
+
+
+def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet: int, multi_speaker: bool) -> Dict[str, Tensor]:
+    pk: Dict[str, Tensor] = {
+        "word_emb": g("encoder.src_word_emb.weight").contiguous(),
+        "enc_pos": g("encoder.position_enc")[0].contiguous(),
+        "dec_pos": g("decoder.position_enc")[0].contiguous(),
+        "pitch_bins": g("variance_adaptor.pitch_bins").contiguous(),
+        "energy_bins": g("variance_adaptor.energy_bins").contiguous(),
+        "pitch_emb": g("variance_adaptor.pitch_embedding.weight").contiguous(),
+        "energy_emb": g("variance_adaptor.energy_embedding.weight").contiguous(),
+        "w_mel": lin_w(g("mel_linear.weight")), "b_mel": g("mel_linear.bias").contiguous(),
+    }
+    if multi_speaker:
+        pk["spk_emb"] = g("speaker_emb.weight").contiguous()
+    for i in range(n_enc):
+        for k, v in pack_fft_block(g, f"encoder.layer_stack.{i}").items():
+            pk[f"enc.{i}.{k}"] = v
+    for i in range(n_dec):
+        for k, v in pack_fft_block(g, f"decoder.layer_stack.{i}").items():
+            pk[f"dec.{i}.{k}"] = v
+    for nm in ("dur", "pitch", "energy"):
+        full = {"dur": "duration", "pitch": "pitch", "energy": "energy"}[nm]
+        for k, v in pack_predictor(g, f"variance_adaptor.{full}_predictor").items():
+            pk[f"{nm}.{k}"] = v
+    for i in range(n_postnet):
+        p = f"postnet.convolutions.{i}"
+        wf, bf = fold_batchnorm(g(p + ".0.conv.weight"), g(p + ".0.conv.bias"), g(p + ".1.weight"), g(p + ".1.bias"),
+                                g(p + ".1.running_mean"), g(p + ".1.running_var"))
+        pk[f"post.{i}.w"], pk[f"post.{i}.b"] = conv_w(wf), bf.contiguous()
+    return pk
+
+
+def fold_weight_norm(v: Tensor, gain: Tensor) -> Tensor:
+    """w = g * v / ||v||, norm over every dim but 0 (torch weight_norm dim=0; dim 0 is C_in for ConvTranspose1d)."""
+    nrm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(gain.shape)
+    return v * (gain / nrm)
+
+
+def split_conv_transpose(w: Tensor, u: int):
+    """ConvTranspose1d(k = 2u, stride u, padding u/2) weight [C_in, C_out, k] -> two 2-tap phase-group conv weights.
+
+    out[q*u + p] = sum_t x[t] . W[:, :, (q - t)*u + p + u/2].  With r = p + u/2:
+      p <  u/2 (r <  u): taps x[q-1] * W[..., r+u] and x[q]   * W[..., r]      -> group A, conv pad_left = 1
+      p >= u/2 (r >= u): taps x[q]   * W[..., r]   and x[q+1] * W[..., r-u]    -> group B, conv pad_left = 0
+    Output column (p - p0)*C_out + n of group g lands at element p*C_out + n of the [B][T][u*C_out] == [B][T*u][C_out] row."""
+    cin, cout, k = w.shape
+    if k != 2 * u or u % 2:
+        raise ValueError("needs kernel = 2*stride and even stride")
+    half = u // 2
+    wa = w.new_empty(2, cin, half * cout)
+    wb = w.new_empty(2, cin, half * cout)
+    for p in range(half):
+        r = p + half
+        wa[0, :, p * cout:(p + 1) * cout] = w[:, :, r + u]
+        wa[1, :, p * cout:(p + 1) * cout] = w[:, :, r]
+    for p in range(half, u):
+        r = p + half
+        wb[0, :, (p - half) * cout:(p - half + 1) * cout] = w[:, :, r]
+        wb[1, :, (p - half) * cout:(p - half + 1) * cout] = w[:, :, r - u]
+    return wa.contiguous(), wb.contiguous()
+
+
+def pack_vocoder(w_of: Callable[[str], Tensor], b_of: Callable[[str], Tensor], rates, n_resblocks: int, n_dil: int) -> Dict[str, Tensor]:
+    """`w_of(base)` returns the folded weight of conv `base`, `b_of(base)` its bias."""
+    pk: Dict[str, Tensor] = {"w_pre": conv_w(w_of("conv_pre")), "b_pre": b_of("conv_pre").contiguous()}
+    for i, u in enumerate(rates):
+        wa, wb = split_conv_transpose(w_of(f"ups.{i}"), u)
+        pk[f"up.{i}.wa"], pk[f"up.{i}.wb"] = wa, wb
+        pk[f"up.{i}.b"] = b_of(f"ups.{i}").repeat(u).contiguous()
+    for rb in range(n_resblocks):
+        for d in range(n_dil):
+            pk[f"rb.{rb}.{d}.w1"] = conv_w(w_of(f"resblocks.{rb}.convs1.{d}"))
+            pk[f"rb.{rb}.{d}.b1"] = b_of(f"resblocks.{rb}.convs1.{d}").contiguous()
+            pk[f"rb.{rb}.{d}.w2"] = conv_w(w_of(f"resblocks.{rb}.convs2.{d}"))
+            pk[f"rb.{rb}.{d}.b2"] = b_of(f"resblocks.{rb}.convs2.{d}").contiguous()
+    pk["w_post"] = w_of("conv_post")[0].t().contiguous()      # [1, C, 7] -> [7][C]
+    pk["b_post"] = b_of("conv_post").contiguous()
+    return pk

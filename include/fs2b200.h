@@ -1,0 +1,241 @@
+/* fs2b200.h -- C ABI of the B200-native FastSpeech2 + HiFi-GAN inference path.
+ *
+ * The reference (ming024/FastSpeech2) has no FFI: its "plugin API" for this path is two nn.Module
+ * classes.  This library is what a native binding underneath those two classes calls:
+ *
+ *   fs2_acoustic_encode  + fs2_acoustic_decode   replace  model.fastspeech2.FastSpeech2.forward
+ *                                                 (model/fastspeech2.py:43-110; split at the one
+ *                                                 data-dependent shape, max(mel_len), modules.py:136)
+ *   fs2_vocoder_forward                           replaces hifigan.models.Generator.forward
+ *                                                 (hifigan/models.py:149-165)
+ *
+ * plus one entry point per fused operator (used by the model-level calls and by the parity tests):
+ *
+ *   fs2_embed_positions   transformer/Models.py:89-91        fs2_conv1d        nn.Conv1d / nn.Linear / ConvTranspose1d call sites
+ *   fs2_attention         transformer/Modules.py:14-25       fs2_layernorm     nn.LayerNorm + masked_fill (Layers.py:25,28)
+ *   fs2_variance_head     model/modules.py:80-100,:246-250   fs2_durations     model/modules.py:132-135,:185-187
+ *   fs2_length_regulate   model/modules.py:167-194           fs2_conv_post     hifigan/models.py:161-163
+ *
+ * Conventions: every pointer is a DEVICE pointer unless named *_host; activations are fp32,
+ * channels-last ([B][T][C], C contiguous); the library never allocates, frees or synchronises --
+ * the caller provides outputs and a workspace and owns the stream.  Return value: FS2_OK or a
+ * negative error; a CUDA launch error e is returned as FS2_ERR_CUDA - e.  No exceptions, no exit().
+ */
+#ifndef FS2B200_H
+#define FS2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fs2_stream_t; /* cudaStream_t */
+
+enum {
+  FS2_OK = 0,
+  FS2_ERR_ARG = -1,         /* null pointer / non-positive size / misaligned pointer */
+  FS2_ERR_UNSUPPORTED = -2, /* configuration outside what the kernels specialise on */
+  FS2_ERR_WORKSPACE = -3,   /* workspace too small */
+  FS2_ERR_CUDA = -1000      /* FS2_ERR_CUDA - cudaError_t */
+};
+
+enum { FS2_ACT_NONE = 0, FS2_ACT_RELU = 1, FS2_ACT_TANH = 2, FS2_ACT_LRELU = 3 };
+
+#define FS2_MAX_LAYERS 12
+#define FS2_MAX_POSTNET 8
+#define FS2_MAX_STAGES 8
+#define FS2_MAX_RESBLOCKS 32
+#define FS2_MAX_DIL 4
+
+/* ------------------------------------------------------------------ operators */
+
+/* y[b,t,n] = (accumulate ? y : 0) + alpha * ( out_act( bias[n] + sum_{j<taps} sum_c in_act(x[b, t + j*dilation - pad_left, c]) * w[j][c][n] ) + res[b,t,n] )
+ * rows outside [0,T) read as zero (Conv1d zero padding); rows t >= row_lens[b] are written as exact 0 when row_lens != NULL.
+ * Strides are in elements.  Covers nn.Linear (taps=1), nn.Conv1d (any odd k, dilation), and one phase group of
+ * ConvTranspose1d (two taps, y_row_stride = u*C_out; see fs2_vocoder_model). */
+typedef struct fs2_conv1d_args {
+  const float* x; int64_t x_batch_stride, x_row_stride;
+  int B, T, Cin;
+  const float* w;    /* [taps][Cin][N] */
+  const float* bias; /* [N] or NULL */
+  int N, taps, dilation, pad_left;
+  int in_act; float in_slope;
+  int out_act; float out_slope;
+  const float* res; int64_t res_batch_stride, res_row_stride; /* NULL = none */
+  float alpha; int accumulate;
+  const int32_t* row_lens; /* [B] or NULL */
+  float* y; int64_t y_batch_stride, y_row_stride;
+} fs2_conv1d_args;
+int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t stream);
+
+/* y = LayerNorm_C(x) * gamma + beta over the last dim, then rows t >= row_lens[b] := 0.  x,y contiguous [B][T][C]; C%4==0, C<=1024. */
+typedef struct fs2_layernorm_args {
+  const float* x; float* y; int B, T, C;
+  const float* gamma; const float* beta; float eps;
+  const int32_t* row_lens; /* [B] or NULL */
+} fs2_layernorm_args;
+int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t stream);
+
+/* ctx[b,t,h*Dh+j] = sum_s softmax_s( q[b,t,h,:].k[b,s,h,:] * scale , keys s >= key_lens[b] masked ) * v[b,s,h,j]
+ * qkv: [B][T][3*H*Dh] rows laid out q|k|v, heads contiguous inside each.  Dh must be 128.  Query rows t >= key_lens[b] are written as 0
+ * (the reference zeroes them after the following LayerNorm, transformer/Layers.py:25). */
+typedef struct fs2_attention_args {
+  const float* qkv; float* ctx; int B, T, H, Dh;
+  const int32_t* key_lens; float scale;
+} fs2_attention_args;
+int fs2_attention(const fs2_attention_args* a, fs2_stream_t stream);
+
+/* y[b,l,:] = table[ids[b,l]] + pos[l]   (+ spk[speakers[b]] when spk != NULL: not used by the encoder, kept for tests) */
+typedef struct fs2_embed_args {
+  const int64_t* ids; const float* table; const float* pos; float* y; int B, L, D, n_vocab;
+} fs2_embed_args;
+int fs2_embed_positions(const fs2_embed_args* a, fs2_stream_t stream);
+
+/* x[b,l,:] += table[idx[b]]  for every l < L (padded rows included, model/fastspeech2.py:68-71) */
+typedef struct fs2_rowbias_args { float* x; const float* table; const int64_t* idx; int B, L, D, n_rows; } fs2_rowbias_args;
+int fs2_add_speaker(const fs2_rowbias_args* a, fs2_stream_t stream);
+
+/* pred[b,l] = (h[b,l,:].w + *b), 0 where l >= lens[b]; if bins != NULL:
+ *   v = target ? target[b,l] : pred*control (pred_out then holds the scaled value),  i = #edges < v (torch.bucketize right=False),
+ *   x[b,l,:] += emb[i]. */
+typedef struct fs2_variance_head_args {
+  const float* h; const float* w; const float* b; int B, L, C;
+  const int32_t* lens; float control; const float* target;
+  const float* bins; int n_edges; const float* emb; int D; float* x;
+  float* pred_out;
+} fs2_variance_head_args;
+int fs2_variance_head(const fs2_variance_head_args* a, fs2_stream_t stream);
+
+/* d = use_target ? src[b,l] : max(rint(exp(src[b,l]) - 1) * d_control, 0); reps = max((int)d, 0);
+ * cum[b,l] = inclusive prefix sum of reps; mel_lens[b] = cum[b,L-1]; len_stats[0] = max_b mel_lens, [1] = sum_b mel_lens
+ * (len_stats must be zeroed by the caller or pass zero_stats=1). */
+typedef struct fs2_durations_args {
+  const float* src; int use_target; float d_control; int B, L;
+  float* d_rounded;     /* [B][L] or NULL */
+  int32_t* cum;         /* [B][L] */
+  int64_t* mel_lens;    /* [B] */
+  int32_t* mel_lens32;  /* [B] or NULL */
+  int32_t* len_stats;   /* [2] */
+} fs2_durations_args;
+int fs2_durations(const fs2_durations_args* a, fs2_stream_t stream);
+
+/* y[b,t,:] = (t < cum[b,L-1] ? x[b, upper_bound(cum[b,:], t), :] : 0) + (pos ? pos[t,:] : 0),  t < T */
+typedef struct fs2_length_regulate_args {
+  const float* x; const int32_t* cum; const float* pos; float* y; int B, L, T, D;
+} fs2_length_regulate_args;
+int fs2_length_regulate(const fs2_length_regulate_args* a, fs2_stream_t stream);
+
+/* wav[b,t] = tanh( *bias + sum_{j<taps} sum_c lrelu_slope(x[b,t+j-pad,c]) * w[j][c] )   (hifigan/models.py:161-163) */
+typedef struct fs2_conv_post_args {
+  const float* x; int B, T, C; const float* w; const float* bias; int taps; float in_slope; float* wav;
+} fs2_conv_post_args;
+int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t stream);
+
+/* out[b,t,c] = in[b,c,t]  (mel [B,80,T] -> channels-last) */
+int fs2_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, fs2_stream_t stream);
+
+/* ------------------------------------------------------------------ acoustic model (FastSpeech2.forward) */
+
+typedef struct fs2_fft_block_weights {
+  const float *w_qkv, *b_qkv;   /* [D][3D], [3D]   (w_qs|w_ks|w_vs transposed and concatenated) */
+  const float *w_o, *b_o;       /* [D][D]          (fc) */
+  const float *ln1_g, *ln1_b;
+  const float *w_1, *b_1;       /* [k1][D][F]      (pos_ffn.w_1) */
+  const float *w_2, *b_2;       /* [k2][F][D] */
+  const float *ln2_g, *ln2_b;
+} fs2_fft_block_weights;
+
+typedef struct fs2_predictor_weights {
+  const float *w_c1, *b_c1, *ln1_g, *ln1_b; /* [k][D][F] */
+  const float *w_c2, *b_c2, *ln2_g, *ln2_b; /* [k][F][F] */
+  const float *w_out, *b_out;               /* [F], [1] */
+} fs2_predictor_weights;
+
+typedef struct fs2_acoustic_model {
+  int d_model, n_head, d_inner, k1, k2, n_enc, n_dec, n_mel;
+  int vp_filter, vp_kernel, n_bins, n_vocab, n_speakers;
+  int enc_pos_rows, dec_pos_rows;            /* rows available in the position tables */
+  const float *word_emb, *enc_pos, *dec_pos, *spk_emb;
+  fs2_fft_block_weights enc[FS2_MAX_LAYERS], dec[FS2_MAX_LAYERS];
+  fs2_predictor_weights dur, pitch, energy;
+  const float *pitch_bins, *energy_bins, *pitch_emb, *energy_emb;
+  const float *w_mel, *b_mel;                /* [D][n_mel] */
+  int n_postnet, post_k;
+  int post_cin[FS2_MAX_POSTNET], post_cout[FS2_MAX_POSTNET];
+  const float *w_post[FS2_MAX_POSTNET], *b_post[FS2_MAX_POSTNET]; /* BatchNorm folded in: [k][cin][cout] */
+} fs2_acoustic_model;
+
+/* Phase 1: encoder + speaker add + variance adaptor up to the duration prefix sums. */
+typedef struct fs2_encode_args {
+  int B, L;
+  const int64_t* texts;      /* [B][L] */
+  const int64_t* speakers;   /* [B] (ignored when the model has no speaker table) */
+  const int32_t* src_lens;   /* [B] */
+  float p_control, e_control, d_control;
+  const float *p_target, *e_target, *d_target; /* [B][L] or NULL */
+  float *p_pred, *e_pred, *logd_pred, *d_rounded; /* [B][L] outputs (d_rounded unused with d_target) */
+  int64_t* mel_lens;         /* [B] */
+  int32_t* mel_lens32;       /* [B] */
+  int32_t* cum_dur;          /* [B][L] */
+  float* x_adapted;          /* [B][L][D]: input of the length regulator */
+  int32_t* len_stats;        /* device [2]: max and sum of mel_lens */
+  int32_t* len_stats_host;   /* pinned host [2] or NULL: async D2H copy is enqueued on the stream */
+  void* workspace; size_t workspace_bytes;
+} fs2_encode_args;
+size_t fs2_encode_workspace_bytes(const fs2_acoustic_model* m, int B, int L);
+int fs2_acoustic_encode(const fs2_acoustic_model* m, const fs2_encode_args* a, fs2_stream_t stream);
+
+/* Phase 2: length regulator + decoder + mel_linear + PostNet (+ residual). */
+typedef struct fs2_decode_args {
+  int B, L, T;
+  const float* x_adapted; const int32_t* cum_dur;
+  const int32_t* mel_mask_lens;  /* [B]: rows t >= len are padding for the decoder masks */
+  float* mel; float* postnet_mel; /* [B][T][n_mel] */
+  void* workspace; size_t workspace_bytes;
+} fs2_decode_args;
+size_t fs2_decode_workspace_bytes(const fs2_acoustic_model* m, int B, int T);
+int fs2_acoustic_decode(const fs2_acoustic_model* m, const fs2_decode_args* a, fs2_stream_t stream);
+
+/* ------------------------------------------------------------------ vocoder (hifigan Generator.forward) */
+
+typedef struct fs2_vocoder_model {
+  int n_mel, c0, n_stages, n_kernels, n_dil;
+  int rates[FS2_MAX_STAGES], up_k[FS2_MAX_STAGES];
+  int rb_k[FS2_MAX_DIL + 4]; int rb_dil[FS2_MAX_DIL + 4][FS2_MAX_DIL];
+  const float *w_pre, *b_pre;                                   /* [7][n_mel][c0] */
+  /* ConvTranspose1d(k = 2u) as two 2-tap phase-group convolutions writing [B][T][u*C_out]:
+   *   group A: output phases p < u/2 read x[q-1], x[q];  group B: phases p >= u/2 read x[q], x[q+1]. */
+  const float *w_up_a[FS2_MAX_STAGES], *w_up_b[FS2_MAX_STAGES]; /* [2][C_in][(u/2)*C_out] */
+  const float *b_up[FS2_MAX_STAGES];                            /* [u*C_out] (bias tiled per phase) */
+  const float *w_rb1[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *b_rb1[FS2_MAX_RESBLOCKS][FS2_MAX_DIL]; /* [k][C][C] */
+  const float *w_rb2[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *b_rb2[FS2_MAX_RESBLOCKS][FS2_MAX_DIL];
+  const float *w_post, *b_post;                                 /* [7][C_last], [1] */
+} fs2_vocoder_model;
+
+typedef struct fs2_vocoder_args {
+  int B, T;
+  const float* mel; int64_t mel_batch_stride, mel_row_stride; /* channels-last view [B][T][n_mel] */
+  float* wav;                                                  /* [B][T*prod(rates)] */
+  void* workspace; size_t workspace_bytes;
+} fs2_vocoder_args;
+size_t fs2_vocoder_workspace_bytes(const fs2_vocoder_model* m, int B, int T);
+int fs2_vocoder_forward(const fs2_vocoder_model* m, const fs2_vocoder_args* a, fs2_stream_t stream);
+
+/* ------------------------------------------------------------------ misc */
+int fs2_abi_version(void);                 /* bumps when any struct above changes */
+int64_t fs2_kernel_launch_count(void);     /* kernels launched by this library since load (process-wide) */
+const char* fs2_build_info(void);          /* "sm_100a ..." */
+size_t fs2_struct_size(int which);
+/* Per-kernel-class device timing for bench.py's roofline (CUDA events recorded around each launch on the launch stream).
+ * Classes: 0 conv1d (implicit GEMM), 1 attention, 2 layernorm, 3 everything else.  begin() arms it, end() synchronises the
+ * recorded events, fills ms/flops/launches per class (arrays of FS2_PROF_CLASSES) and disarms.  Not for timed regions. */
+#define FS2_PROF_CLASSES 4
+int fs2_profile_begin(void);
+int fs2_profile_end(double* ms, double* flops, int64_t* launches);         /* sizeof of the i-th struct above, in declaration order (binding self-check) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2B200_H */

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference (absent on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def scratch(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("fs2cfg"))
+
+
+@pytest.fixture(scope="session")
+def lj_configs(scratch):
+    from fastspeech2_b200 import configs
+    return configs.make_configs("LJSpeech", scratch)
+
+
+@pytest.fixture(scope="session")
+def libri_configs(scratch):
+    from fastspeech2_b200 import configs
+    return configs.make_configs("LibriTTS", scratch)

@@ -1,0 +1,142 @@
+"""GPU: the two drop-in modules against the CPU oracle on identical inputs and weights.
+
+Protocol (hard part 2): (A) free-running -- continuous predictions are compared and the discrete
+decisions (durations, hence mel_lens) must match exactly; (B) teacher-forced with the oracle's own decisions so a
+boundary flip cannot hide or fake a mel error.  Bars from BASELINE.json: mel 1e-3, waveform 1e-4 max-abs."""
+import pytest
+import torch
+
+from fastspeech2_b200 import configs, synth
+from fastspeech2_b200.hifigan import AttrDict, Generator
+from fastspeech2_b200.model import FastSpeech2
+from oracle import fs2_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+MEL_TOL, WAV_TOL = 1e-3, 1e-4
+
+
+def _model(cfgs, seed):
+    pc, mc = cfgs
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=seed)
+    m = FastSpeech2(pc, mc)
+    m.load_state_dict(sd)
+    return m.to(DEV).eval(), sd
+
+
+def _cmp(out, ref):
+    errs = {}
+    for i, name in ((0, "mel"), (1, "postnet"), (2, "pitch"), (3, "energy"), (4, "logd")):
+        errs[name] = (out[i].cpu() - ref[i]).abs().max().item()
+    return errs
+
+
+@pytest.mark.parametrize("B,L,min_len", [(1, 24, None), (3, 40, 17), (16, 128, None)])
+def test_fastspeech2_free_running_lj(lj_configs, B, L, min_len):
+    m, sd = _model(lj_configs, seed=1)
+    spk, texts, lens, Lm = synth.make_batch(B, L, seed=2, min_len=min_len)
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm)
+    out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm)
+    assert torch.equal(out[5].cpu(), ref[5]), "duration decisions differ"
+    assert torch.equal(out[9].cpu(), ref[9]) and torch.equal(out[6].cpu(), ref[6]) and torch.equal(out[7].cpu(), ref[7])
+    e = _cmp(out, ref)
+    assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL and max(e["pitch"], e["energy"], e["logd"]) < 1e-4, e
+
+
+def test_fastspeech2_multispeaker_controls(libri_configs):
+    m, sd = _model(libri_configs, seed=3)
+    spk, texts, lens, Lm = synth.make_batch(5, 64, seed=4, n_speakers=904, min_len=20)
+    kw = dict(p_control=1.15, e_control=0.8, d_control=1.3)
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm, **kw)
+    out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm, **kw)
+    assert torch.equal(out[5].cpu(), ref[5]) and torch.equal(out[9].cpu(), ref[9])
+    e = _cmp(out, ref)
+    assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
+
+
+def test_fastspeech2_teacher_forced(lj_configs):
+    m, sd = _model(lj_configs, seed=5)
+    spk, texts, lens, Lm = synth.make_batch(4, 48, seed=6, min_len=15)
+    free = O.fastspeech2_forward(sd, spk, texts, lens, Lm)
+    d_t, mel_lens = free[5].long(), free[9]
+    T = int(mel_lens.max())
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm, None, mel_lens, T, free[2], free[3], d_t)
+    out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm, None, mel_lens.to(DEV), T, free[2].to(DEV), free[3].to(DEV), d_t.to(DEV))
+    e = _cmp(out, ref)
+    assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
+    assert torch.equal(out[9].cpu(), ref[9])
+
+
+def test_fastspeech2_long_sequence_position_table(lj_configs):
+    """T > max_seq_len (1000): eval mode recomputes the sinusoid table and never truncates (Models.py:145-152)."""
+    pc, mc = lj_configs
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=7, frames_per_phoneme=11.0)
+    m = FastSpeech2(pc, mc); m.load_state_dict(sd); m = m.to(DEV).eval()
+    spk, texts, lens, Lm = synth.make_batch(2, 120, seed=8, min_len=60)
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm)
+    assert int(ref[9].max()) > 1000
+    out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm)
+    assert torch.equal(out[9].cpu(), ref[9])
+    e = _cmp(out, ref)
+    assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
+
+
+def test_fastspeech2_golden_vs_reference(lj_configs, libri_configs):
+    """Committed outputs of the UNMODIFIED reference (tests/golden/, made by oracle/gen_golden.py)."""
+    import numpy as np, os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    for name, cfgs in (("fs2_lj", lj_configs), ("fs2_libri", libri_configs)):
+        z = np.load(os.path.join(gdir, name + ".npz"))
+        m, sd = _model(cfgs, seed=int(z["seed"]))
+        t = lambda k: torch.from_numpy(z[k])
+        out = m(t("speakers").to(DEV), t("texts").to(DEV), t("src_lens").to(DEV), int(z["max_src_len"]),
+                p_control=float(z["p_control"]), e_control=float(z["e_control"]), d_control=float(z["d_control"]))
+        assert torch.equal(out[9].cpu(), t("mel_lens")) and torch.equal(out[5].cpu(), t("d_rounded"))
+        assert (out[0].cpu() - t("mel")).abs().max() < MEL_TOL
+        assert (out[1].cpu() - t("postnet_mel")).abs().max() < MEL_TOL
+
+
+def _generator(seed):
+    h = AttrDict(configs.HIFIGAN_CONFIG)
+    sd = synth.hifigan_state_dict(h, seed=seed)
+    gen = Generator(h)
+    gen.load_state_dict(sd)
+    gen.eval()
+    gen.remove_weight_norm()
+    return gen.to(DEV), sd
+
+
+@pytest.mark.parametrize("B,T", [(1, 7), (2, 50), (3, 129)])
+def test_hifigan_vs_oracle(B, T):
+    gen, sd = _generator(seed=1)
+    mel = synth.make_mel(B, T, seed=2)
+    want = O.hifigan_forward(sd, mel)
+    got = gen(mel.to(DEV))
+    assert got.shape == want.shape
+    assert (got.cpu() - want).abs().max() < WAV_TOL
+    # the usual caller passes a transposed channels-last view (utils/tools.py:202)
+    view = mel.transpose(1, 2).contiguous().to(DEV).transpose(1, 2)
+    assert (gen(view).cpu() - want).abs().max() < WAV_TOL
+
+
+def test_hifigan_golden_vs_reference():
+    import numpy as np, os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hifigan.npz"))
+    gen, _ = _generator(seed=int(z["seed"]))
+    got = gen(torch.from_numpy(z["mel"]).to(DEV))
+    assert (got.cpu() - torch.from_numpy(z["wav"])).abs().max() < WAV_TOL
+
+
+def test_end_to_end_wav(lj_configs):
+    m, sd = _model(lj_configs, seed=9)
+    gen, hsd = _generator(seed=3)
+    spk, texts, lens, Lm = synth.make_batch(2, 32, seed=10, min_len=20)
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm)
+    out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm)
+    assert torch.equal(out[9].cpu(), ref[9])
+    want = O.hifigan_forward(hsd, ref[1].transpose(1, 2))
+    got = gen(out[1].transpose(1, 2))
+    # waveform bar applies to the vocoder given the same mel; end to end the mel error (<=1e-3) propagates, so compare both ways
+    same_mel = gen(ref[1].to(DEV).transpose(1, 2))
+    assert (same_mel.cpu() - want).abs().max() < WAV_TOL
+    assert (got.cpu() - want).abs().max() < 5e-3

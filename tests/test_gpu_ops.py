@@ -1,0 +1,181 @@
+"""GPU: every C-ABI operator against its CPU contract (tests/emul_cabi.py, torch fp32 on CPU).  fp32 kernels: the only
+difference allowed is summation order, so tolerances are a few ulp of the accumulated magnitude."""
+import pytest
+import torch
+
+from fastspeech2_b200 import ops, packing
+from tests import emul_cabi as E
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def g(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=g(seed)) * scale
+
+
+CONV_CASES = [
+    # B, T, Cin, N, taps, dil, pad, in_act, out_act, res, alpha, accumulate, lens
+    (2, 200, 256, 768, 1, 1, 0, 0, 0, False, 1.0, False, False),     # QKV projection
+    (2, 131, 256, 1024, 9, 1, 4, 0, 1, False, 1.0, False, False),    # conv-FFN w_1 + ReLU
+    (2, 131, 1024, 256, 1, 1, 0, 0, 0, True, 1.0, False, False),     # conv-FFN w_2 + residual
+    (3, 77, 80, 512, 5, 1, 2, 0, 2, False, 1.0, False, False),       # PostNet first conv + tanh
+    (3, 77, 512, 80, 5, 1, 2, 0, 0, True, 1.0, False, False),        # PostNet last conv + mel residual (N = 80)
+    (1, 300, 128, 128, 11, 5, 25, 3, 3, False, 1.0, False, False),   # HiFi-GAN resblock conv1 (dilated, lrelu in/out)
+    (2, 260, 64, 64, 7, 1, 3, 0, 0, True, 1.0 / 3, True, False),     # resblock conv2 accumulate into stage sum
+    (2, 515, 32, 32, 3, 3, 3, 3, 3, False, 1.0, False, False),       # last stage, N = 32
+    (2, 140, 256, 256, 3, 1, 1, 0, 1, False, 1.0, False, True),      # with row masking
+    (1, 1, 256, 256, 3, 1, 1, 0, 0, False, 1.0, False, False),       # single row
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv1d(case):
+    B, T, Cin, N, taps, dil, pad, in_act, out_act, use_res, alpha, acc, use_lens = case
+    x = rnd(B, T, Cin, seed=1)
+    w = rnd(taps, Cin, N, seed=2, scale=(taps * Cin) ** -0.5)
+    bias = rnd(N, seed=3, scale=0.1)
+    res = rnd(B, T, N, seed=4) if use_res else None
+    y0 = rnd(B, T, N, seed=5) if acc else None
+    lens = torch.tensor([max(1, T - 7 * (i + 1)) for i in range(B)], dtype=torch.int32) if use_lens else None
+    want = E.conv1d(x, w, bias, dil, pad, in_act, 0.1, out_act, 0.1, res, alpha, y0, lens)
+    out = y0.to(DEV).clone() if acc else None
+    got = ops.conv1d(x.to(DEV), w.to(DEV), bias.to(DEV), dilation=dil, pad_left=pad, in_act=in_act, in_slope=0.1, out_act=out_act,
+                     out_slope=0.1, res=None if res is None else res.to(DEV), alpha=alpha, out=out, accumulate=acc,
+                     row_lens=None if lens is None else lens.to(DEV))
+    torch.cuda.synchronize()
+    err = (got.cpu() - want).abs().max().item()
+    assert err < 2e-5, err
+
+
+def test_conv1d_strided_output_conv_transpose():
+    for u, cin, cout, T in ((8, 64, 32, 37), (2, 64, 32, 130)):
+        w = rnd(cin, cout, 2 * u, seed=7, scale=0.1)
+        x = rnd(2, T, cin, seed=8)
+        bias = rnd(cout, seed=9, scale=0.1)
+        want = torch.nn.functional.conv_transpose1d(torch.nn.functional.leaky_relu(x, 0.1).transpose(1, 2), w, bias, stride=u,
+                                                    padding=u // 2).transpose(1, 2)
+        wa, wb = packing.split_conv_transpose(w, u)
+        half = u // 2
+        out = torch.empty(2, T, u * cout, device=DEV)
+        bt = bias.repeat(u).to(DEV)
+        xd = x.to(DEV)
+        ops.conv1d(xd, wa.to(DEV), bt[: half * cout], pad_left=1, in_act=3, in_slope=0.1, out=out[:, :, : half * cout])
+        ops.conv1d(xd, wb.to(DEV), bt[half * cout:], pad_left=0, in_act=3, in_slope=0.1, out=out[:, :, half * cout:])
+        torch.cuda.synchronize()
+        err = (out.cpu().reshape(2, T * u, cout) - want).abs().max().item()
+        assert err < 2e-5, err
+
+
+def test_conv1d_rejects_bad_shapes():
+    from fastspeech2_b200._lib import Fs2Error
+    x = torch.zeros(1, 8, 24, device=DEV)          # Cin % 16 != 0
+    w = torch.zeros(1, 24, 16, device=DEV)
+    with pytest.raises(Fs2Error):
+        ops.conv1d(x, w)
+
+
+@pytest.mark.parametrize("C", [256, 512, 1024, 80])
+def test_layernorm(C):
+    x = rnd(3, 50, C, seed=1, scale=3.0) + 0.5
+    gm, bt = 1 + rnd(C, seed=2, scale=0.1), rnd(C, seed=3, scale=0.1)
+    lens = torch.tensor([50, 13, 1], dtype=torch.int32)
+    for ln_ in (None, lens):
+        want = E.layernorm(x, gm, bt, ln_)
+        got = ops.layernorm(x.to(DEV), gm.to(DEV), bt.to(DEV), None if ln_ is None else ln_.to(DEV))
+        assert (got.cpu() - want).abs().max() < 5e-6
+
+
+@pytest.mark.parametrize("T,lens", [(130, [130, 64, 1]), (64, [64, 64, 33]), (257, [257, 200, 65])])
+def test_attention(T, lens):
+    qkv = rnd(3, T, 768, seed=1)
+    kl = torch.tensor(lens, dtype=torch.int32)
+    want = E.attention(qkv, 2, kl)
+    got = ops.attention(qkv.to(DEV), 2, kl.to(DEV))
+    torch.cuda.synchronize()
+    assert (got.cpu() - want).abs().max() < 5e-6
+
+
+def test_embed_and_speaker():
+    table = rnd(361, 256, seed=1)
+    pos = rnd(1001, 256, seed=2)
+    ids = torch.randint(0, 361, (4, 37), generator=g(3))
+    y = ops.embed_positions(ids.to(DEV), table.to(DEV), pos.to(DEV))
+    assert torch.equal(y.cpu(), table[ids] + pos[:37])
+    spk = rnd(904, 256, seed=4)
+    sid = torch.randint(0, 904, (4,), generator=g(5))
+    y2 = ops.add_speaker_(y.clone(), spk.to(DEV), sid.to(DEV))
+    assert torch.equal(y2.cpu(), (table[ids] + pos[:37]) + spk[sid][:, None, :])
+
+
+def test_variance_head():
+    h = rnd(3, 40, 256, seed=1)
+    w, b = rnd(256, seed=2, scale=0.1), torch.tensor([0.3])
+    lens = torch.tensor([40, 25, 3], dtype=torch.int32)
+    bins = torch.linspace(-2.9, 11.4, 255)
+    emb = rnd(256, 256, seed=3)
+    x = rnd(3, 40, 256, seed=4)
+    tgt = rnd(3, 40, seed=5, scale=3.0)
+    # duration-style (no bins)
+    want, _ = E.variance_head(h, w, b, lens, 1.0, None, None, None, None)
+    got = ops.variance_head(h.to(DEV), w.to(DEV), b.to(DEV), lens.to(DEV))
+    assert (got.cpu() - want).abs().max() < 2e-6
+    for target, control in ((None, 1.3), (tgt, 1.0)):
+        wp, wx = E.variance_head(h, w, b, lens, control, target, bins, emb, x)
+        xd = x.to(DEV).clone()
+        gp = ops.variance_head(h.to(DEV), w.to(DEV), b.to(DEV), lens.to(DEV), control, None if target is None else target.to(DEV),
+                               bins.to(DEV), emb.to(DEV), xd)
+        assert (gp.cpu() - wp).abs().max() < 2e-6
+        assert (xd.cpu() - wx).abs().max() < 1e-6     # same buckets picked
+
+
+def test_bucketize_edges_exact():
+    """torch.bucketize(right=False): a value equal to an edge goes to that edge's index."""
+    bins = torch.linspace(-1.0, 1.0, 255)
+    vals = torch.cat([bins[[0, 1, 100, 254]], torch.tensor([-5.0, 5.0, 0.0])])
+    n = vals.numel()
+    h = torch.zeros(1, n, 4); h[0, :, 0] = vals
+    w = torch.tensor([1.0, 0, 0, 0]); b = torch.zeros(1)
+    emb = torch.arange(256, dtype=torch.float32)[:, None].repeat(1, 4)
+    x = torch.zeros(1, n, 4, device=DEV)
+    ops.variance_head(h.to(DEV), w.to(DEV), b.to(DEV), None, 1.0, None, bins.to(DEV), emb.to(DEV), x)
+    assert torch.equal(x[0, :, 0].cpu().long(), torch.bucketize(vals, bins))
+
+
+@pytest.mark.parametrize("L,d_control", [(40, 1.0), (300, 2.5), (1000, 0.7)])
+def test_durations_and_length_regulate(L, d_control):
+    B = 3
+    logd = rnd(B, L, seed=1, scale=0.6) + 1.2
+    logd[1, L // 2:] = 0.0                                    # padded phonemes predict log-duration 0 -> d = 0
+    logd[0, :5] = torch.log(torch.tensor([3.5, 4.5, 1.5, 2.5, 1.0]))   # round-half-even cases
+    wd, wcum, wlen = E.durations(logd, False, d_control)
+    d, cum, mel_lens, mel_lens32, stats = ops.durations(logd.to(DEV), False, d_control)
+    assert torch.equal(d.cpu(), wd) and torch.equal(cum.cpu(), wcum) and torch.equal(mel_lens.cpu(), wlen)
+    assert stats.cpu().tolist() == [int(wlen.max()), int(wlen.sum())]
+    x = rnd(B, L, 256, seed=2)
+    pos = rnd(int(wlen.max()) + 8, 256, seed=3)
+    for T in (int(wlen.max()), int(wlen.max()) + 5):
+        want = E.length_regulate(x, wcum, pos, T)
+        got = ops.length_regulate(x.to(DEV), cum, T, pos.to(DEV))
+        assert torch.equal(got.cpu(), want)                   # gather + one add: bit exact
+    # integer targets (teacher forcing)
+    tgt = torch.randint(0, 9, (B, L), generator=g(4)).float()
+    _, wcum2, wlen2 = E.durations(tgt, True, 1.0)
+    _, cum2, ml2, _, _ = ops.durations(tgt.to(DEV), True, 1.0)
+    assert torch.equal(cum2.cpu(), wcum2) and torch.equal(ml2.cpu(), wlen2)
+
+
+def test_conv_post_and_transpose():
+    x = rnd(2, 700, 32, seed=1)
+    w = rnd(7, 32, seed=2, scale=0.1)
+    b = torch.tensor([0.05])
+    xa = torch.where(x > 0, x, x * 0.01)
+    want = torch.tanh(torch.nn.functional.conv1d(xa.transpose(1, 2), w.t()[None], b, padding=3))[:, 0]
+    got = ops.conv_post(x.to(DEV), w.to(DEV), b.to(DEV), 0.01)
+    assert (got.cpu() - want).abs().max() < 2e-6
+    m = rnd(3, 80, 45, seed=3)
+    assert torch.equal(ops.transpose_bct_to_btc(m.to(DEV)).cpu(), m.transpose(1, 2).contiguous())
