@@ -11,9 +11,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS, MAX_POSTNET, MAX_STAGES, MAX_RESBLOCKS, MAX_DIL = 12, 8, 8, 32, 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
+CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
+TC_ENCODER, TC_PREDICTORS, TC_DECODER, TC_POSTNET = 1, 2, 4, 8
 
 fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 i32, i64, f32 = C.c_int, C.c_int64, C.c_float
@@ -24,6 +26,7 @@ class Conv1dArgs(C.Structure):
                 ("B", i32), ("T", i32), ("Cin", i32),
                 ("w", fp), ("bias", fp),
                 ("N", i32), ("taps", i32), ("dilation", i32), ("pad_left", i32),
+                ("w_tc", fp), ("backend", i32), ("tc_variant", C.c_uint),
                 ("in_act", i32), ("in_slope", f32), ("out_act", i32), ("out_slope", f32),
                 ("res", fp), ("res_batch_stride", i64), ("res_row_stride", i64),
                 ("alpha", f32), ("accumulate", i32),
@@ -71,7 +74,8 @@ class ConvPostArgs(C.Structure):
 
 
 class FftBlockWeights(C.Structure):
-    _fields_ = [(n, fp) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "ln1_g", "ln1_b", "w_1", "b_1", "w_2", "b_2", "ln2_g", "ln2_b")]
+    _fields_ = [(n, fp) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "ln1_g", "ln1_b", "w_1", "b_1", "w_2", "b_2", "ln2_g", "ln2_b",
+                                  "w_qkv_tc", "w_o_tc", "w_1_tc", "w_2_tc")]
 
 
 class PredictorWeights(C.Structure):
@@ -81,7 +85,7 @@ class PredictorWeights(C.Structure):
 class AcousticModel(C.Structure):
     _fields_ = [("d_model", i32), ("n_head", i32), ("d_inner", i32), ("k1", i32), ("k2", i32), ("n_enc", i32), ("n_dec", i32),
                 ("n_mel", i32), ("vp_filter", i32), ("vp_kernel", i32), ("n_bins", i32), ("n_vocab", i32), ("n_speakers", i32),
-                ("enc_pos_rows", i32), ("dec_pos_rows", i32),
+                ("enc_pos_rows", i32), ("dec_pos_rows", i32), ("tc_mask", i32),
                 ("word_emb", fp), ("enc_pos", fp), ("dec_pos", fp), ("spk_emb", fp),
                 ("enc", FftBlockWeights * MAX_LAYERS), ("dec", FftBlockWeights * MAX_LAYERS),
                 ("dur", PredictorWeights), ("pitch", PredictorWeights), ("energy", PredictorWeights),
@@ -89,7 +93,8 @@ class AcousticModel(C.Structure):
                 ("w_mel", fp), ("b_mel", fp),
                 ("n_postnet", i32), ("post_k", i32),
                 ("post_cin", i32 * MAX_POSTNET), ("post_cout", i32 * MAX_POSTNET),
-                ("w_post", fp * MAX_POSTNET), ("b_post", fp * MAX_POSTNET)]
+                ("w_post", fp * MAX_POSTNET), ("b_post", fp * MAX_POSTNET),
+                ("w_mel_tc", fp), ("w_post_tc", fp * MAX_POSTNET)]
 
 
 class EncodeArgs(C.Structure):
@@ -115,7 +120,9 @@ class VocoderModel(C.Structure):
                 ("w_up_a", fp * MAX_STAGES), ("w_up_b", fp * MAX_STAGES), ("b_up", fp * MAX_STAGES),
                 ("w_rb1", (fp * MAX_DIL) * MAX_RESBLOCKS), ("b_rb1", (fp * MAX_DIL) * MAX_RESBLOCKS),
                 ("w_rb2", (fp * MAX_DIL) * MAX_RESBLOCKS), ("b_rb2", (fp * MAX_DIL) * MAX_RESBLOCKS),
-                ("w_post", fp), ("b_post", fp)]
+                ("w_post", fp), ("b_post", fp),
+                ("w_pre_tc", fp), ("w_up_a_tc", fp * MAX_STAGES), ("w_up_b_tc", fp * MAX_STAGES),
+                ("w_rb1_tc", (fp * MAX_DIL) * MAX_RESBLOCKS), ("w_rb2_tc", (fp * MAX_DIL) * MAX_RESBLOCKS)]
 
 
 class VocoderArgs(C.Structure):
@@ -132,6 +139,7 @@ EXPORTS = {
     "fs2_profile_begin": (i32, []),
     "fs2_profile_end": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "fs2_conv1d": (i32, [C.POINTER(Conv1dArgs), fp]),
+    "fs2_conv_tc_block": (i32, [i32]),
     "fs2_layernorm": (i32, [C.POINTER(LayerNormArgs), fp]),
     "fs2_attention": (i32, [C.POINTER(AttentionArgs), fp]),
     "fs2_embed_positions": (i32, [C.POINTER(EmbedArgs), fp]),

@@ -30,6 +30,17 @@ void prof_after(cudaStream_t s, int cls, double flops) {
 
 // kernels / launchers defined in the other translation units
 int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s);
+int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s);
+bool conv_tc_supported(const fs2_conv1d_args* a);
+int conv_tc_nb(int N);
+
+// backend dispatch of the fs2_conv1d contract
+static int conv1d_dispatch(const fs2_conv1d_args* a, cudaStream_t s) {
+  if (!a) return FS2_ERR_ARG;
+  if (a->backend == FS2_CONV_TC) return a->w_tc ? conv1d_tc(a, a->w_tc, a->tc_variant, s) : FS2_ERR_ARG;
+  if (a->backend == FS2_CONV_AUTO && a->w_tc && conv_tc_supported(a)) return conv1d_tc(a, a->w_tc, a->tc_variant, s);
+  return conv1d_simt(a, s);
+}
 int attention_simt(const fs2_attention_args* a, cudaStream_t s);
 int embed_positions(const fs2_embed_args* a, cudaStream_t s);
 int add_speaker(const fs2_rowbias_args* a, cudaStream_t s);
@@ -56,10 +67,12 @@ struct Arena {
 };
 
 // contiguous [B][T][C] convolution helper
-static int conv(cudaStream_t s, const float* x, int B, int T, int Cin, const float* w, const float* bias, int N, int taps,
-                int dil, int pad, int out_act, float out_slope, float* y, const float* res = nullptr, int in_act = FS2_ACT_NONE,
-                float in_slope = 0.f, float alpha = 1.f, int accumulate = 0, const int32_t* row_lens = nullptr) {
+static int conv(cudaStream_t s, const float* x, int B, int T, int Cin, const float* w, const float* w_tc, const float* bias, int N,
+                int taps, int dil, int pad, int out_act, float out_slope, float* y, const float* res = nullptr,
+                int in_act = FS2_ACT_NONE, float in_slope = 0.f, float alpha = 1.f, int accumulate = 0,
+                const int32_t* row_lens = nullptr) {
   fs2_conv1d_args a{};
+  a.w_tc = w_tc; a.backend = FS2_CONV_AUTO;
   a.x = x; a.x_batch_stride = (int64_t)T * Cin; a.x_row_stride = Cin;
   a.B = B; a.T = T; a.Cin = Cin;
   a.w = w; a.bias = bias; a.N = N; a.taps = taps; a.dilation = dil; a.pad_left = pad;
@@ -67,7 +80,7 @@ static int conv(cudaStream_t s, const float* x, int B, int T, int Cin, const flo
   a.res = res; a.res_batch_stride = (int64_t)T * N; a.res_row_stride = N;
   a.alpha = alpha; a.accumulate = accumulate; a.row_lens = row_lens;
   a.y = y; a.y_batch_stride = (int64_t)T * N; a.y_row_stride = N;
-  return conv1d_simt(&a, s);
+  return conv1d_dispatch(&a, s);
 }
 
 static int ln(cudaStream_t s, const float* x, float* y, int B, int T, int C, const float* g, const float* b, const int32_t* lens) {
@@ -79,15 +92,16 @@ struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; };
 
 // One FFT block in place on bufs.x  (transformer/Layers.py:21-30)
 static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_block_weights& w, const FftBufs& f, int B, int T,
-                     const int32_t* lens) {
+                     const int32_t* lens, bool tc) {
   const int D = m->d_model, F = m->d_inner;
-  FS2_TRY(conv(s, f.x, B, T, D, w.w_qkv, w.b_qkv, 3 * D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.qkv));
+  const float* none = nullptr;
+  FS2_TRY(conv(s, f.x, B, T, D, w.w_qkv, tc ? w.w_qkv_tc : none, w.b_qkv, 3 * D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.qkv));
   fs2_attention_args at{f.qkv, f.ctx, B, T, m->n_head, D / m->n_head, lens, 1.0f / sqrtf((float)(D / m->n_head))};
   FS2_TRY(attention_simt(&at, s));
-  FS2_TRY(conv(s, f.ctx, B, T, D, w.w_o, w.b_o, D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.tmp, f.x));
+  FS2_TRY(conv(s, f.ctx, B, T, D, w.w_o, tc ? w.w_o_tc : none, w.b_o, D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.tmp, f.x));
   FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln1_g, w.ln1_b, lens));
-  FS2_TRY(conv(s, f.x, B, T, D, w.w_1, w.b_1, F, m->k1, 1, (m->k1 - 1) / 2, FS2_ACT_RELU, 0.f, f.hid));
-  FS2_TRY(conv(s, f.hid, B, T, F, w.w_2, w.b_2, D, m->k2, 1, (m->k2 - 1) / 2, FS2_ACT_NONE, 0.f, f.tmp, f.x));
+  FS2_TRY(conv(s, f.x, B, T, D, w.w_1, tc ? w.w_1_tc : none, w.b_1, F, m->k1, 1, (m->k1 - 1) / 2, FS2_ACT_RELU, 0.f, f.hid));
+  FS2_TRY(conv(s, f.hid, B, T, F, w.w_2, tc ? w.w_2_tc : none, w.b_2, D, m->k2, 1, (m->k2 - 1) / 2, FS2_ACT_NONE, 0.f, f.tmp, f.x));
   FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln2_g, w.ln2_b, lens));
   return FS2_OK;
 }
@@ -121,7 +135,7 @@ static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cu
 
   fs2_embed_args e{a->texts, m->word_emb, m->enc_pos, f.x, B, L, D, m->n_vocab};
   FS2_TRY(embed_positions(&e, s));
-  for (int i = 0; i < m->n_enc; i++) FS2_TRY(fft_block(s, m, m->enc[i], f, B, L, a->src_lens));
+  for (int i = 0; i < m->n_enc; i++) FS2_TRY(fft_block(s, m, m->enc[i], f, B, L, a->src_lens, (m->tc_mask & FS2_TC_ENCODER) != 0));
   if (m->spk_emb) {
     if (!a->speakers) return FS2_ERR_ARG;
     fs2_rowbias_args r{f.x, m->spk_emb, a->speakers, B, L, D, m->n_speakers};
@@ -134,9 +148,9 @@ static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cu
   auto predictor = [&](const fs2_predictor_weights& w, const float* x, float control, const float* target, const float* bins,
                        const float* emb, float* pred_out) -> int {
     const int k = m->vp_kernel;
-    FS2_TRY(conv(s, x, B, L, D, w.w_c1, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
+    FS2_TRY(conv(s, x, B, L, D, w.w_c1, nullptr, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
     FS2_TRY(ln(s, h1, h2, B, L, VF, w.ln1_g, w.ln1_b, nullptr));
-    FS2_TRY(conv(s, h2, B, L, VF, w.w_c2, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
+    FS2_TRY(conv(s, h2, B, L, VF, w.w_c2, nullptr, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
     FS2_TRY(ln(s, h1, h2, B, L, VF, w.ln2_g, w.ln2_b, nullptr));
     fs2_variance_head_args v{};
     v.h = h2; v.w = w.w_out; v.b = w.b_out; v.B = B; v.L = L; v.C = VF;
@@ -176,14 +190,16 @@ static int decode_impl(const fs2_acoustic_model* m, const fs2_decode_args* a, cu
 
   fs2_length_regulate_args lr{a->x_adapted, a->cum_dur, m->dec_pos, f.x, B, a->L, T, D};
   FS2_TRY(length_regulate(&lr, s));
-  for (int i = 0; i < m->n_dec; i++) FS2_TRY(fft_block(s, m, m->dec[i], f, B, T, a->mel_mask_lens));
-  FS2_TRY(conv(s, f.x, B, T, D, m->w_mel, m->b_mel, m->n_mel, 1, 1, 0, FS2_ACT_NONE, 0.f, a->mel));
+  for (int i = 0; i < m->n_dec; i++) FS2_TRY(fft_block(s, m, m->dec[i], f, B, T, a->mel_mask_lens, (m->tc_mask & FS2_TC_DECODER) != 0));
+  const bool tcp = (m->tc_mask & FS2_TC_POSTNET) != 0;
+  FS2_TRY(conv(s, f.x, B, T, D, m->w_mel, tcp ? m->w_mel_tc : nullptr, m->b_mel, m->n_mel, 1, 1, 0, FS2_ACT_NONE, 0.f, a->mel));
   // PostNet: eval BatchNorm folded into (w, b) by the packer; unmasked, tanh on all but the last (Layers.py:129-137)
   const float* cur = a->mel;
   for (int i = 0; i < m->n_postnet; i++) {
     const bool last = i == m->n_postnet - 1;
     float* dst = last ? a->postnet_mel : ((i & 1) ? pb : pa);
-    FS2_TRY(conv(s, cur, B, T, m->post_cin[i], m->w_post[i], m->b_post[i], m->post_cout[i], m->post_k, 1, (m->post_k - 1) / 2,
+    FS2_TRY(conv(s, cur, B, T, m->post_cin[i], m->w_post[i], tcp ? m->w_post_tc[i] : nullptr, m->b_post[i], m->post_cout[i], m->post_k, 1,
+                 (m->post_k - 1) / 2,
                  last ? FS2_ACT_NONE : FS2_ACT_TANH, 0.f, dst, last ? a->mel : nullptr));
     cur = dst;
   }
@@ -214,9 +230,10 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
   {  // conv_pre reads the (possibly strided) channels-last mel view
     fs2_conv1d_args c{};
     c.x = a->mel; c.x_batch_stride = a->mel_batch_stride; c.x_row_stride = a->mel_row_stride;
-    c.B = B; c.T = T; c.Cin = m->n_mel; c.w = m->w_pre; c.bias = m->b_pre; c.N = m->c0; c.taps = 7; c.dilation = 1; c.pad_left = 3;
+    c.B = B; c.T = T; c.Cin = m->n_mel; c.w = m->w_pre; c.w_tc = m->w_pre_tc; c.bias = m->b_pre; c.N = m->c0; c.taps = 7;
+    c.dilation = 1; c.pad_left = 3;
     c.alpha = 1.f; c.y = bx; c.y_batch_stride = (int64_t)T * m->c0; c.y_row_stride = m->c0;
-    FS2_TRY(conv1d_simt(&c, s));
+    FS2_TRY(conv1d_dispatch(&c, s));
   }
   int Ti = T, C = m->c0;
   const float inv_nk = 1.f / (float)m->n_kernels;
@@ -228,11 +245,12 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
       fs2_conv1d_args c{};
       c.x = bx; c.x_batch_stride = (int64_t)Ti * C; c.x_row_stride = C; c.B = B; c.T = Ti; c.Cin = C;
       c.w = g == 0 ? m->w_up_a[i] : m->w_up_b[i];
+      c.w_tc = g == 0 ? m->w_up_a_tc[i] : m->w_up_b_tc[i];
       c.bias = m->b_up[i] + (size_t)g * (u / 2) * Co;
       c.N = (u / 2) * Co; c.taps = 2; c.dilation = 1; c.pad_left = g == 0 ? 1 : 0;
       c.in_act = FS2_ACT_LRELU; c.in_slope = 0.1f; c.alpha = 1.f;
       c.y = bu + (size_t)g * (u / 2) * Co; c.y_batch_stride = (int64_t)Ti * u * Co; c.y_row_stride = (int64_t)u * Co;
-      FS2_TRY(conv1d_simt(&c, s));
+      FS2_TRY(conv1d_dispatch(&c, s));
     }
     Ti *= u; C = Co;
     // ---- mean of the multi-receptive-field ResBlocks (models.py:154-160, ResBlock.forward :96-103)
@@ -241,12 +259,12 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
       const float* r = bu;
       for (int d = 0; d < m->n_dil; d++) {
         const int dil = m->rb_dil[j][d];
-        FS2_TRY(conv(s, r, B, Ti, C, m->w_rb1[rb][d], m->b_rb1[rb][d], C, k, dil, (k * dil - dil) / 2, FS2_ACT_LRELU, 0.1f, bt, nullptr,
-                     FS2_ACT_LRELU, 0.1f));
+        FS2_TRY(conv(s, r, B, Ti, C, m->w_rb1[rb][d], m->w_rb1_tc[rb][d], m->b_rb1[rb][d], C, k, dil, (k * dil - dil) / 2, FS2_ACT_LRELU,
+                     0.1f, bt, nullptr, FS2_ACT_LRELU, 0.1f));
         const bool last = d == m->n_dil - 1;
         float* dst = last ? bx : (r == r1 ? r2 : r1);
-        FS2_TRY(conv(s, bt, B, Ti, C, m->w_rb2[rb][d], m->b_rb2[rb][d], C, k, 1, (k - 1) / 2, FS2_ACT_NONE, 0.f, dst, r, FS2_ACT_NONE,
-                     0.f, last ? inv_nk : 1.f, last && j > 0));
+        FS2_TRY(conv(s, bt, B, Ti, C, m->w_rb2[rb][d], m->w_rb2_tc[rb][d], m->b_rb2[rb][d], C, k, 1, (k - 1) / 2, FS2_ACT_NONE, 0.f, dst,
+                     r, FS2_ACT_NONE, 0.f, last ? inv_nk : 1.f, last && j > 0));
         r = dst;
       }
     }
@@ -263,7 +281,8 @@ using namespace fs2;
 
 extern "C" {
 
-int fs2_abi_version(void) { return 1; }
+int fs2_abi_version(void) { return 2; }
+int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count; }
 size_t fs2_struct_size(int which) {
   switch (which) {
@@ -306,9 +325,9 @@ int fs2_profile_end(double* ms, double* flops, int64_t* launches) {
   g_prof.clear();
   return rc;
 }
-const char* fs2_build_info(void) { return "fs2b200 sm_100a fp32-simt path, built " __DATE__ " " __TIME__; }
+const char* fs2_build_info(void) { return "fs2b200 sm_100a (tcgen05 3xTF32 conv + fp32 CUDA-core kernels), built " __DATE__ " " __TIME__; }
 
-int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t st) { return conv1d_simt(a, S(st)); }
+int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t st) { return conv1d_dispatch(a, S(st)); }
 int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t st) { return layernorm(a, S(st)); }
 int fs2_attention(const fs2_attention_args* a, fs2_stream_t st) { return attention_simt(a, S(st)); }
 int fs2_embed_positions(const fs2_embed_args* a, fs2_stream_t st) { return embed_positions(a, S(st)); }

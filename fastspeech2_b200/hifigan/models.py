@@ -32,6 +32,7 @@ class Generator(nn.Module):
         self.num_kernels = len(self._hd["resblock_kernel_sizes"])
         self.num_upsamples = len(self._hd["upsample_rates"])
         self._weight_norm = True
+        self.use_tensor_cores = True     # 3xTF32 tcgen05 kernel for every conv it supports; False = fp32 CUDA-core kernels only
         populate(self, hifigan_spec(self._hd, weight_norm=True))
         with torch.no_grad():  # g = ||v|| so that the initial folded weight equals v, as torch's weight_norm does
             for base in self._bases():
@@ -109,12 +110,16 @@ class Generator(nn.Module):
                                   hd["upsample_rates"], m.n_stages * m.n_kernels, m.n_dil)
         P = lambda k: pk[k].data_ptr()
         m.w_pre, m.b_pre, m.w_post, m.b_post = P("w_pre"), P("b_pre"), P("w_post"), P("b_post")
+        T = lambda k: pk[k + "_tc"].data_ptr() if (self.use_tensor_cores and k + "_tc" in pk) else 0
+        m.w_pre_tc = T("w_pre")
         for i in range(m.n_stages):
             m.w_up_a[i], m.w_up_b[i], m.b_up[i] = P(f"up.{i}.wa"), P(f"up.{i}.wb"), P(f"up.{i}.b")
+            m.w_up_a_tc[i], m.w_up_b_tc[i] = T(f"up.{i}.wa"), T(f"up.{i}.wb")
         for rb in range(m.n_stages * m.n_kernels):
             for d in range(m.n_dil):
                 m.w_rb1[rb][d], m.b_rb1[rb][d] = P(f"rb.{rb}.{d}.w1"), P(f"rb.{rb}.{d}.b1")
                 m.w_rb2[rb][d], m.b_rb2[rb][d] = P(f"rb.{rb}.{d}.w2"), P(f"rb.{rb}.{d}.b2")
+                m.w_rb1_tc[rb][d], m.w_rb2_tc[rb][d] = T(f"rb.{rb}.{d}.w1"), T(f"rb.{rb}.{d}.w2")
         up = 1
         for u in hd["upsample_rates"]:
             up *= u

@@ -49,6 +49,9 @@ class FastSpeech2(nn.Module):
                         torch.exp(torch.linspace(np.log(stats["energy"][0]), np.log(stats["energy"][1]), n)))
         self.multi_speaker = bool(model_config["multi_speaker"])
         self.max_seq_len = int(model_config["max_seq_len"])
+        # Which sub-networks may run on the 3xTF32 tensor-core kernel.  Encoder and predictors stay on the exact fp32 kernels:
+        # they feed the discrete duration / pitch-bucket decisions (hard part 2) and are <1% of the FLOPs.
+        self.tc_mask = L.TC_DECODER | L.TC_POSTNET
         self._packed = None          # (AcousticModel struct, keep-alive tensors, device)
         self._pos_long = {}          # device position tables longer than max_seq_len, keyed by width
         self._ws = None
@@ -106,15 +109,19 @@ class FastSpeech2(nn.Module):
             for i in range(n):
                 dst = getattr(m, side)[i]
                 for name, _ in L.FftBlockWeights._fields_:
-                    setattr(dst, name, P(f"{side}.{i}.{name}"))
+                    key = f"{side}.{i}.{name}"
+                    setattr(dst, name, P(key) if key in pk else 0)
         for nm in ("dur", "pitch", "energy"):
             dst = getattr(m, nm)
             for name, _ in L.PredictorWeights._fields_:
                 setattr(dst, name, P(f"{nm}.{name}"))
         for name in ("pitch_bins", "energy_bins", "pitch_emb", "energy_emb", "w_mel", "b_mel"):
             setattr(m, name, P(name))
+        m.tc_mask = self.tc_mask
+        m.w_mel_tc = P("w_mel_tc") if "w_mel_tc" in pk else 0
         m.n_postnet = n_post
         for i in range(n_post):
+            m.w_post_tc[i] = P(f"post.{i}.w_tc") if f"post.{i}.w_tc" in pk else 0
             w = pk[f"post.{i}.w"]                      # [k][cin][cout]
             m.w_post[i], m.b_post[i] = w.data_ptr(), P(f"post.{i}.b")
             m.post_k, m.post_cin[i], m.post_cout[i] = w.shape[0], w.shape[1], w.shape[2]

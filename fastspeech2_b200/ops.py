@@ -19,7 +19,7 @@ def _need_cuda(t):
 
 
 def conv1d(x, w, bias=None, *, dilation=1, pad_left=0, in_act=L.ACT_NONE, in_slope=0.0, out_act=L.ACT_NONE, out_slope=0.0,
-           res=None, alpha=1.0, out=None, accumulate=False, row_lens=None):
+           res=None, alpha=1.0, out=None, accumulate=False, row_lens=None, w_tc=None, backend=L.CONV_AUTO, tc_variant=0):
     """x [B,T,Cin] (row-strided ok), w [taps][Cin][N] -> y [B,T,N].  `out` may be a strided [B,T,N] view."""
     _need_cuda(x)
     B, T, Cin = x.shape
@@ -29,6 +29,7 @@ def conv1d(x, w, bias=None, *, dilation=1, pad_left=0, in_act=L.ACT_NONE, in_slo
     assert x.stride(2) == 1 and out.stride(2) == 1 and w.is_contiguous()
     a = L.Conv1dArgs(x=x.data_ptr(), x_batch_stride=x.stride(0), x_row_stride=x.stride(1), B=B, T=T, Cin=Cin,
                      w=w.data_ptr(), bias=L.ptr(bias), N=N, taps=taps, dilation=dilation, pad_left=pad_left,
+                     w_tc=L.ptr(w_tc), backend=backend, tc_variant=tc_variant,
                      in_act=in_act, in_slope=in_slope, out_act=out_act, out_slope=out_slope,
                      res=L.ptr(res), res_batch_stride=res.stride(0) if res is not None else 0,
                      res_row_stride=res.stride(1) if res is not None else 0,

@@ -23,6 +23,46 @@ def lin_w(w: Tensor) -> Tensor:
     return w.t().contiguous()
 
 
+def conv_tc_block(n_out: int) -> int:
+    """Output channels per CTA of the tcgen05 kernel (mirror of conv_tc_nb in csrc/conv_tc.cu); 0 = unsupported."""
+    if n_out <= 256:
+        return n_out if n_out % 16 == 0 else 0
+    for nb in range(256, 15, -16):
+        if n_out % nb == 0:
+            return nb
+    return 0
+
+
+def split_tf32(w: Tensor):
+    """x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi exact in fp32."""
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+def pack_conv_tc(w: Tensor):
+    """[taps][Cin][N] -> tcgen05 tile layout [N/NB][taps][Cin/16][hi|lo][4 K-chunks][NB][4 floats] (see include/fs2b200.h).
+    Returns None when the shape is not served by the tensor-core kernel."""
+    taps, cin, n = w.shape
+    nb = conv_tc_block(n)
+    if nb == 0 or cin % 16:
+        return None
+    hi, lo = split_tf32(w)
+    both = torch.stack([hi, lo], dim=0)                                  # [2][taps][Cin][N]
+    t = both.reshape(2, taps, cin // 16, 4, 4, n // nb, nb)              # [2][tap][kb][chunk][e][nblk][nn]
+    return t.permute(5, 1, 2, 0, 3, 6, 4).contiguous()                   # [nblk][tap][kb][2][chunk][nn][e]
+
+
+def add_tc_tiles(pk: Dict[str, Tensor], keys) -> None:
+    """For every packed conv weight key in `keys` add '<key>_tc' when the tensor-core kernel can take it."""
+    for k in keys:
+        w = pk[k]
+        if w.dim() == 2:
+            w = w[None]
+        t = pack_conv_tc(w)
+        if t is not None:
+            pk[k + "_tc"] = t
+
+
 def pack_fft_block(g: Callable[[str], Tensor], pfx: str) -> Dict[str, Tensor]:
     a, f = pfx + ".slf_attn.", pfx + ".pos_ffn."
     return {
@@ -83,6 +123,8 @@ def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet:
         wf, bf = fold_batchnorm(g(p + ".0.conv.weight"), g(p + ".0.conv.bias"), g(p + ".1.weight"), g(p + ".1.bias"),
                                 g(p + ".1.running_mean"), g(p + ".1.running_var"))
         pk[f"post.{i}.w"], pk[f"post.{i}.b"] = conv_w(wf), bf.contiguous()
+    tc_keys = [f"{side}.{i}.{w}" for side, n in (("enc", n_enc), ("dec", n_dec)) for i in range(n) for w in ("w_qkv", "w_o", "w_1", "w_2")]
+    add_tc_tiles(pk, tc_keys + ["w_mel"] + [f"post.{i}.w" for i in range(n_postnet)])
     return pk
 
 
@@ -131,4 +173,6 @@ def pack_vocoder(w_of: Callable[[str], Tensor], b_of: Callable[[str], Tensor], r
             pk[f"rb.{rb}.{d}.b2"] = b_of(f"resblocks.{rb}.convs2.{d}").contiguous()
     pk["w_post"] = w_of("conv_post")[0].t().contiguous()      # [1, C, 7] -> [7][C]
     pk["b_post"] = b_of("conv_post").contiguous()
+    add_tc_tiles(pk, ["w_pre"] + [f"up.{i}.{g}" for i in range(len(rates)) for g in ("wa", "wb")]
+                 + [f"rb.{rb}.{d}.{w}" for rb in range(n_resblocks) for d in range(n_dil) for w in ("w1", "w2")])
     return pk

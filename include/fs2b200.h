@@ -42,6 +42,15 @@ enum {
 };
 
 enum { FS2_ACT_NONE = 0, FS2_ACT_RELU = 1, FS2_ACT_TANH = 2, FS2_ACT_LRELU = 3 };
+enum { FS2_CONV_AUTO = 0, FS2_CONV_SIMT = 1, FS2_CONV_TC = 2 };
+/* which parts of the acoustic model may use the 3xTF32 tensor-core kernel (fs2_acoustic_model.tc_mask) */
+enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POSTNET = 8 };
+
+/* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per CTA,
+ * hi = w & 0xffffe000 (a TF32 value), lo = w - hi, the tiled buffer is
+ *     [N/NB][taps][Cin/16][2: hi,lo][4: 16-byte K chunk][NB][4 floats]
+ * i.e. every (tap, 16-channel K-block) stage is one contiguous 128*NB-byte smem image (UMMA no-swizzle K-major). */
+int fs2_conv_tc_block(int N); /* 0 when N is not supported by the tensor-core kernel */
 
 #define FS2_MAX_LAYERS 12
 #define FS2_MAX_POSTNET 8
@@ -61,6 +70,9 @@ typedef struct fs2_conv1d_args {
   const float* w;    /* [taps][Cin][N] */
   const float* bias; /* [N] or NULL */
   int N, taps, dilation, pad_left;
+  const float* w_tc; /* NULL, or the same weights in the tcgen05 tile layout (see "tensor-core weight tiles" below) */
+  int backend;       /* FS2_CONV_AUTO: tcgen05 3xTF32 kernel when w_tc is given and the shape qualifies, else the fp32 CUDA-core kernel */
+  unsigned tc_variant; /* 0; debug knob for descriptor bring-up */
   int in_act; float in_slope;
   int out_act; float out_slope;
   const float* res; int64_t res_batch_stride, res_row_stride; /* NULL = none */
@@ -145,6 +157,7 @@ typedef struct fs2_fft_block_weights {
   const float *w_1, *b_1;       /* [k1][D][F]      (pos_ffn.w_1) */
   const float *w_2, *b_2;       /* [k2][F][D] */
   const float *ln2_g, *ln2_b;
+  const float *w_qkv_tc, *w_o_tc, *w_1_tc, *w_2_tc; /* tensor-core tiles of the four weights, or NULL */
 } fs2_fft_block_weights;
 
 typedef struct fs2_predictor_weights {
@@ -157,6 +170,7 @@ typedef struct fs2_acoustic_model {
   int d_model, n_head, d_inner, k1, k2, n_enc, n_dec, n_mel;
   int vp_filter, vp_kernel, n_bins, n_vocab, n_speakers;
   int enc_pos_rows, dec_pos_rows;            /* rows available in the position tables */
+  int tc_mask;                               /* FS2_TC_* bits; parts not selected run the fp32 CUDA-core kernels */
   const float *word_emb, *enc_pos, *dec_pos, *spk_emb;
   fs2_fft_block_weights enc[FS2_MAX_LAYERS], dec[FS2_MAX_LAYERS];
   fs2_predictor_weights dur, pitch, energy;
@@ -165,6 +179,7 @@ typedef struct fs2_acoustic_model {
   int n_postnet, post_k;
   int post_cin[FS2_MAX_POSTNET], post_cout[FS2_MAX_POSTNET];
   const float *w_post[FS2_MAX_POSTNET], *b_post[FS2_MAX_POSTNET]; /* BatchNorm folded in: [k][cin][cout] */
+  const float *w_mel_tc, *w_post_tc[FS2_MAX_POSTNET];             /* tensor-core tiles or NULL */
 } fs2_acoustic_model;
 
 /* Phase 1: encoder + speaker add + variance adaptor up to the duration prefix sums. */
@@ -212,6 +227,9 @@ typedef struct fs2_vocoder_model {
   const float *w_rb1[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *b_rb1[FS2_MAX_RESBLOCKS][FS2_MAX_DIL]; /* [k][C][C] */
   const float *w_rb2[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *b_rb2[FS2_MAX_RESBLOCKS][FS2_MAX_DIL];
   const float *w_post, *b_post;                                 /* [7][C_last], [1] */
+  /* tensor-core tiles (NULL = CUDA-core kernel for that conv) */
+  const float *w_pre_tc, *w_up_a_tc[FS2_MAX_STAGES], *w_up_b_tc[FS2_MAX_STAGES];
+  const float *w_rb1_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *w_rb2_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL];
 } fs2_vocoder_model;
 
 typedef struct fs2_vocoder_args {

@@ -28,3 +28,16 @@ def lj_configs(scratch):
 def libri_configs(scratch):
     from fastspeech2_b200 import configs
     return configs.make_configs("LibriTTS", scratch)
+
+
+@pytest.fixture(scope="session")
+def parity_log():
+    """Append max-abs errors to gpurun_out/parity_report.jsonl (when that directory exists) so the margins are on record."""
+    import json
+    path = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
+
+    def log(test, **vals):
+        if os.path.isdir(os.path.dirname(path)):
+            with open(path, "a") as f:
+                f.write(json.dumps({"test": test, **{k: (float(v) if hasattr(v, "__float__") else v) for k, v in vals.items()}}) + "\n")
+    return log

@@ -32,7 +32,7 @@ def _cmp(out, ref):
 
 
 @pytest.mark.parametrize("B,L,min_len", [(1, 24, None), (3, 40, 17), (16, 128, None)])
-def test_fastspeech2_free_running_lj(lj_configs, B, L, min_len):
+def test_fastspeech2_free_running_lj(lj_configs, B, L, min_len, parity_log):
     m, sd = _model(lj_configs, seed=1)
     spk, texts, lens, Lm = synth.make_batch(B, L, seed=2, min_len=min_len)
     ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm)
@@ -40,10 +40,11 @@ def test_fastspeech2_free_running_lj(lj_configs, B, L, min_len):
     assert torch.equal(out[5].cpu(), ref[5]), "duration decisions differ"
     assert torch.equal(out[9].cpu(), ref[9]) and torch.equal(out[6].cpu(), ref[6]) and torch.equal(out[7].cpu(), ref[7])
     e = _cmp(out, ref)
+    parity_log(f"fs2_free_running_lj_B{B}_L{L}", **e)
     assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL and max(e["pitch"], e["energy"], e["logd"]) < 1e-4, e
 
 
-def test_fastspeech2_multispeaker_controls(libri_configs):
+def test_fastspeech2_multispeaker_controls(libri_configs, parity_log):
     m, sd = _model(libri_configs, seed=3)
     spk, texts, lens, Lm = synth.make_batch(5, 64, seed=4, n_speakers=904, min_len=20)
     kw = dict(p_control=1.15, e_control=0.8, d_control=1.3)
@@ -51,10 +52,11 @@ def test_fastspeech2_multispeaker_controls(libri_configs):
     out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm, **kw)
     assert torch.equal(out[5].cpu(), ref[5]) and torch.equal(out[9].cpu(), ref[9])
     e = _cmp(out, ref)
+    parity_log("fs2_multispeaker_controls_B5_L64", **e)
     assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
 
 
-def test_fastspeech2_teacher_forced(lj_configs):
+def test_fastspeech2_teacher_forced(lj_configs, parity_log):
     m, sd = _model(lj_configs, seed=5)
     spk, texts, lens, Lm = synth.make_batch(4, 48, seed=6, min_len=15)
     free = O.fastspeech2_forward(sd, spk, texts, lens, Lm)
@@ -63,6 +65,7 @@ def test_fastspeech2_teacher_forced(lj_configs):
     ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm, None, mel_lens, T, free[2], free[3], d_t)
     out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm, None, mel_lens.to(DEV), T, free[2].to(DEV), free[3].to(DEV), d_t.to(DEV))
     e = _cmp(out, ref)
+    parity_log("fs2_teacher_forced_B4_L48", **e)
     assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
     assert torch.equal(out[9].cpu(), ref[9])
 
@@ -107,12 +110,18 @@ def _generator(seed):
 
 
 @pytest.mark.parametrize("B,T", [(1, 7), (2, 50), (3, 129)])
-def test_hifigan_vs_oracle(B, T):
+def test_hifigan_vs_oracle(B, T, parity_log):
     gen, sd = _generator(seed=1)
     mel = synth.make_mel(B, T, seed=2)
     want = O.hifigan_forward(sd, mel)
     got = gen(mel.to(DEV))
     assert got.shape == want.shape
+    want64 = O.hifigan_forward(sd, mel, dtype=torch.float64)
+    gen.use_tensor_cores = False; gen._invalidate()
+    simt = gen(mel.to(DEV)).cpu()
+    gen.use_tensor_cores = True; gen._invalidate()
+    parity_log(f"hifigan_B{B}_T{T}", wav_vs_oracle32=(got.cpu() - want).abs().max(), wav_vs_oracle64=(got.cpu().double() - want64).abs().max(),
+               simt_vs_oracle32=(simt - want).abs().max(), oracle32_vs_64=(want.double() - want64).abs().max(), peak=want.abs().max())
     assert (got.cpu() - want).abs().max() < WAV_TOL
     # the usual caller passes a transposed channels-last view (utils/tools.py:202)
     view = mel.transpose(1, 2).contiguous().to(DEV).transpose(1, 2)
