@@ -25,8 +25,9 @@ namespace fs2 {
 constexpr int TC_KB = 16;          // input channels per K-block (two K=8 TF32 MMAs)
 constexpr int TC_CHUNKS = TC_KB / 4;
 constexpr int TC_SA = 2;           // activation slab stages
-constexpr int TC_SB = 4;           // weight stages
+constexpr int TC_SB_MAX = 4;       // weight stages (runtime: p.SB <= TC_SB_MAX)
 constexpr int TC_THREADS = 192;
+constexpr int TC_LD = 8;           // 16-byte global loads in flight per transform thread
 
 struct TcP {
   const float* x; long long xbs, xrs;
@@ -43,6 +44,7 @@ struct TcP {
   const int* row_lens;
   float* y; long long ybs, yrs;
   int MT;                          // 128-row tiles per CTA
+  int SB;                          // weight stages in flight
   int R;                           // slab rows held in smem (>= MT*128 + (taps-1)*dil, R % 8 == 2)
   int tiles_per_batch;
   int acc_stride;                  // TMEM columns between accumulators
@@ -101,6 +103,18 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // UMMA shared-memory descriptor, no-swizzle K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
 // LBO = byte distance between the two 16-byte K-chunks of one K=8 (TF32) MMA, SBO = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -117,7 +131,7 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcP p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = p.R, NB = p.NB;
@@ -125,12 +139,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   const uint32_t b_plane = (uint32_t)TC_CHUNKS * NB * 16;         // bytes of one hi (or lo) weight tile
   unsigned char* a_base = smem_raw;                                // [SA][hi|lo][chunk][R][16 B]
   unsigned char* b_base = a_base + (size_t)TC_SA * 2 * a_plane;    // [SB][hi|lo][chunk][NB][16 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)TC_SB * 2 * b_plane);
-  uint64_t* fullA = bars;            // [SA]
-  uint64_t* emptyA = bars + TC_SA;   // [SA]
-  uint64_t* fullB = emptyA + TC_SA;  // [SB]
-  uint64_t* emptyB = fullB + TC_SB;  // [SB]
-  uint64_t* accFull = emptyB + TC_SB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.SB * 2 * b_plane);
+  uint64_t* fullA = bars;                // [SA]
+  uint64_t* emptyA = bars + TC_SA;       // [SA]
+  uint64_t* fullB = emptyA + TC_SA;      // [SB_MAX]
+  uint64_t* emptyB = fullB + TC_SB_MAX;  // [SB_MAX]
+  uint64_t* accFull = emptyB + TC_SB_MAX;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accFull + 1);
 
   const int b = blockIdx.x / p.tiles_per_batch;
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < TC_SA; i++) { mbar_init(&fullA[i], 128); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < TC_SB; i++) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < TC_SB_MAX; i++) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
     mbar_init(accFull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -161,8 +175,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       int it = 0;
       for (int kb = 0; kb < KBLOCKS; kb++) {
         for (int tap = 0; tap < p.taps; tap++, it++) {
-          const int s = it % TC_SB;
-          const uint32_t ph = (it / TC_SB) & 1;
+          const int s = it % p.SB;
+          const uint32_t ph = (it / p.SB) & 1;
           mbar_wait(&emptyB[s], ph ^ 1);
           mbar_expect_tx(&fullB[s], stage_bytes);
           bulk_g2s(b_base + (size_t)s * stage_bytes, wsrc + ((size_t)tap * KBLOCKS + kb) * stage_bytes, stage_bytes, &fullB[s]);
@@ -173,34 +187,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(NB);
-      const bool swap = p.variant & 1u;
-      const uint32_t a_lbo = (uint32_t)R * 16, b_lbo = (uint32_t)NB * 16, sbo = 128;
+      // descriptors differ only in the 14-bit start-address field (16-byte units): build the constant part once and add offsets
+      const uint64_t a_const = umma_desc(0, (uint32_t)R * 16, 128), b_const = umma_desc(0, (uint32_t)NB * 16, 128);
+      const uint32_t a_kk = 2u * (uint32_t)R, b_kk = 2u * (uint32_t)NB;     // two 16-byte K-chunks per K=8 MMA, in 16-byte units
       int it = 0;
       for (int kb = 0; kb < KBLOCKS; kb++) {
         const int sa = kb % TC_SA;
         mbar_wait(&fullA[sa], (kb / TC_SA) & 1);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(a_base + (size_t)sa * 2 * a_plane);
-        const uint32_t a_lo = a_hi + a_plane;
+        const uint64_t a_hi = a_const | (uint64_t)(smem_u32(a_base + (size_t)sa * 2 * a_plane) >> 4);
+        const uint64_t a_lo = a_hi + (a_plane >> 4);
         for (int tap = 0; tap < p.taps; tap++, it++) {
-          const int sb = it % TC_SB;
-          mbar_wait(&fullB[sb], (it / TC_SB) & 1);
+          const int sb = it % p.SB;
+          mbar_wait(&fullB[sb], (it / p.SB) & 1);
           tc_fence_after();
-          const uint32_t b_hi = smem_u32(b_base + (size_t)sb * 2 * b_plane);
-          const uint32_t b_lo = b_hi + b_plane;
-          for (int mt = 0; mt < p.MT; mt++) {
-            const uint32_t row_off = (uint32_t)(mt * 128 + tap * p.dil) * 16;
-            const uint32_t d = tmem + (uint32_t)(mt * p.acc_stride);
+          const uint64_t b_hi = b_const | (uint64_t)(smem_u32(b_base + (size_t)sb * 2 * b_plane) >> 4);
+          const uint64_t b_lo = b_hi + (b_plane >> 4);
+          uint32_t row = (uint32_t)(tap * p.dil);
+          uint32_t d = tmem;
+          for (int mt = 0; mt < p.MT; mt++, row += 128, d += (uint32_t)p.acc_stride) {
 #pragma unroll
             for (int kk = 0; kk < TC_KB / 8; kk++) {
-              const uint32_t ao = row_off + (uint32_t)kk * 2 * a_lbo;
-              const uint32_t bo = (uint32_t)kk * 2 * b_lbo;
-              const uint64_t ah = swap ? umma_desc(a_hi + ao, sbo, a_lbo) : umma_desc(a_hi + ao, a_lbo, sbo);
-              const uint64_t al = swap ? umma_desc(a_lo + ao, sbo, a_lbo) : umma_desc(a_lo + ao, a_lbo, sbo);
-              const uint64_t bh = swap ? umma_desc(b_hi + bo, sbo, b_lbo) : umma_desc(b_hi + bo, b_lbo, sbo);
-              const uint64_t bl = swap ? umma_desc(b_lo + bo, sbo, b_lbo) : umma_desc(b_lo + bo, b_lbo, sbo);
-              const uint32_t first = (kb | tap | kk) ? 1u : 0u;
-              tc_mma_tf32(d, al, bh, idesc, first);   // small terms first
+              const uint64_t ah = a_hi + row + kk * a_kk, al = a_lo + row + kk * a_kk;
+              const uint64_t bh = b_hi + kk * b_kk, bl = b_lo + kk * b_kk;
+              tc_mma_tf32(d, al, bh, idesc, (kb | tap | kk) ? 1u : 0u);   // small terms first
               tc_mma_tf32(d, ah, bl, idesc, 1u);
               tc_mma_tf32(d, ah, bh, idesc, 1u);
             }
@@ -224,10 +234,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       unsigned char* hi = a_base + (size_t)sa * 2 * a_plane;
       unsigned char* lo = hi + a_plane;
       const int c0 = kb * TC_KB;
-      for (int base = 0; base < items; base += 128 * 4) {
-        float4 v[4];
+      for (int base = 0; base < items; base += 128 * TC_LD) {
+        float4 v[TC_LD];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {                  // 4 independent 16-byte loads in flight per thread
+        for (int u = 0; u < TC_LD; u++) {              // TC_LD independent 16-byte loads in flight per thread
           const int idx = base + u * 128 + wt;
           const int row = idx >> 2, ch = idx & 3;
           const int t = t_first + row;
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
           if (idx < items && t >= 0 && t < p.T) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * p.xrs + c0 + ch * 4));
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < TC_LD; u++) {
           const int idx = base + u * 128 + wt;
           if (idx >= items) continue;
           const int row = idx >> 2, ch = idx & 3;
@@ -258,36 +268,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       mbar_arrive(&fullA[sa]);
     }
 
-    // ---- epilogue: TMEM -> registers -> global ----
+    // ---- epilogue: TMEM -> registers -> (per-warp smem transpose) -> coalesced global I/O ----
+    // tcgen05.ld hands each thread one output ROW; writing rows straight out would touch 32 different 128-byte lines per
+    // instruction.  Each warp therefore transposes its 32 x 32 block through a private 32 x 36 float staging tile (the slab
+    // buffers are free once accFull has fired) so that 8 lanes cover one row's 128 bytes: every global load (residual,
+    // accumulate) and store is a full-line access.
     mbar_wait(accFull, 0);
     tc_fence_after();
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int len_b = p.row_lens ? p.row_lens[b] : p.T;
     const int n0 = nblk * NB;
+    float* stage = reinterpret_cast<float*>(a_base) + (warp - 2) * (32 * 36);
     for (int mt = 0; mt < p.MT; mt++) {
-      const int t = t0 + mt * 128 + q * 32 + lane;
-      const bool live = t < p.T;
-      const bool dead = t >= len_b;
-      float* yrow = p.y + (long long)b * p.ybs + (long long)t * p.yrs + n0;
-      const float* rrow = p.res ? (p.res + (long long)b * p.rbs + (long long)t * p.rrs + n0) : nullptr;
-      for (int c = 0; c < NB; c += 16) {
-        uint32_t v[16];
-        tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.acc_stride + c), v);
-        if (!live) continue;
+      const int row_base = t0 + mt * 128 + q * 32;
+      for (int c = 0; c < NB; c += 32) {
+        const int w = (NB - c) >= 32 ? 32 : 16;        // NB % 16 == 0
+        {
+          uint32_t v[32];
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.acc_stride + c);
+          if (w == 32) {
+            tc_ld32(taddr, v);
+          } else {
+            uint32_t v16[16];
+            tc_ld16(taddr, v16);
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-          float o[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            float u = __uint_as_float(v[g * 4 + j]) + (p.bias ? __ldg(p.bias + n0 + c + g * 4 + j) : 0.f);
-            u = apply_act(u, p.out_act, p.out_slope);
-            if (rrow) u += rrow[c + g * 4 + j];
-            u *= p.alpha;
-            if (p.accumulate) u += yrow[c + g * 4 + j];
-            o[j] = dead ? 0.f : u;
+            for (int j = 0; j < 16; j++) v[j] = v16[j];
           }
-          *reinterpret_cast<float4*>(yrow + c + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j * 4 < w)
+              *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =
+                  make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]), __uint_as_float(v[j * 4 + 2]),
+                              __uint_as_float(v[j * 4 + 3]));
         }
+        __syncwarp();
+        const int lpr = w >> 2;                        // lanes per row (8 or 4)
+        const int rpi = 32 / lpr;                      // rows per iteration (4 or 8)
+        const int iters = 32 / rpi;                    // 8 or 4
+        const int rr = lane / lpr, cc = (lane % lpr) * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cc));
+        float4 rv[8], yv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {                  // all global loads of this block in flight before any store
+          rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          yv[k] = rv[k];
+          const int t = row_base + k * rpi + rr;
+          if (k < iters && t < p.T) {
+            const long long off = (long long)t;
+            if (p.res) rv[k] = *reinterpret_cast<const float4*>(p.res + (long long)b * p.rbs + off * p.rrs + n0 + c + cc);
+            if (p.accumulate) yv[k] = *reinterpret_cast<const float4*>(p.y + (long long)b * p.ybs + off * p.yrs + n0 + c + cc);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int r = k * rpi + rr;
+          const int t = row_base + r;
+          if (k < iters && t < p.T) {
+            const float4 a = *reinterpret_cast<const float4*>(stage + r * 36 + cc);
+            float4 o;
+            o.x = (apply_act(a.x + bv.x, p.out_act, p.out_slope) + rv[k].x) * p.alpha + yv[k].x;
+            o.y = (apply_act(a.y + bv.y, p.out_act, p.out_slope) + rv[k].y) * p.alpha + yv[k].y;
+            o.z = (apply_act(a.z + bv.z, p.out_act, p.out_slope) + rv[k].z) * p.alpha + yv[k].z;
+            o.w = (apply_act(a.w + bv.w, p.out_act, p.out_slope) + rv[k].w) * p.alpha + yv[k].w;
+            if (t >= len_b) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(p.y + (long long)b * p.ybs + (long long)t * p.yrs + n0 + c + cc) = o;
+          }
+        }
+        __syncwarp();                                  // staging tile is rewritten by the next block
       }
     }
   }
@@ -307,9 +355,10 @@ static int pow2_cols(int c) {
   return v;
 }
 
-int conv_tc_nb(int N) {  // output channels per CTA
-  if (N <= 256) return (N % 16 == 0) ? N : 0;
-  for (int nb = 256; nb >= 16; nb -= 16)
+int conv_tc_nb(int N) {  // output channels per CTA: at most 128 so that two CTAs (256 TMEM columns each) share an SM
+  if (N % 16) return 0;
+  if (N <= 128) return N;
+  for (int nb = 128; nb >= 16; nb -= 16)
     if (N % nb == 0) return nb;
   return 0;
 }
@@ -342,19 +391,37 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.acc_stride = (p.NB + 31) & ~31;
   const int halo = (a->taps - 1) * a->dilation;
   const int tiles128 = (a->T + 127) / 128;
-  size_t smem = 0;
-  int mt = 512 / p.acc_stride;
-  if (mt > 4) mt = 4;
+  // Two CTAs per SM (one's epilogue / slab load overlaps the other's MMAs): aim for <= ~112 KB of shared memory and <= 256
+  // TMEM columns per CTA; fall back to one CTA per SM when the halo makes the slab too large.
+  const size_t bar_bytes = (2 * TC_SA + 2 * TC_SB_MAX + 1) * 8 + 16;
+  const size_t budget2 = 112 * 1024, budget1 = 226 * 1024;
+  int mt = 256 / p.acc_stride;
+  if (mt > 2) mt = 2;
   if (mt > tiles128) mt = tiles128;
-  for (; mt >= 1; mt--) {
+  if (mt < 1) mt = 1;
+  size_t smem = 0;
+  int sb = 0;
+  for (;; mt--) {
     int R = mt * 128 + halo;
     R += (10 - (R & 7)) & 7;                           // R % 8 == 2: conflict-free transform stores
     p.R = R;
-    smem = (size_t)TC_SA * 2 * TC_CHUNKS * R * 16 + (size_t)TC_SB * 2 * TC_CHUNKS * p.NB * 16 + (2 * TC_SA + 2 * TC_SB + 1) * 8 + 16;
-    if (smem <= 227 * 1024) break;
+    const size_t a_bytes = (size_t)TC_SA * 2 * TC_CHUNKS * R * 16, b_stage = (size_t)2 * TC_CHUNKS * p.NB * 16;
+    for (sb = TC_SB_MAX; sb >= 2; sb--) {
+      smem = a_bytes + sb * b_stage + bar_bytes;
+      if (smem <= budget2) break;
+    }
+    if (sb >= 2) break;
+    if (mt == 1) {                                     // cannot fit two per SM: take what one CTA can have
+      for (sb = TC_SB_MAX; sb >= 2; sb--) {
+        smem = a_bytes + sb * b_stage + bar_bytes;
+        if (smem <= budget1) break;
+      }
+      if (sb < 2) return FS2_ERR_UNSUPPORTED;
+      break;
+    }
   }
-  if (mt < 1) return FS2_ERR_UNSUPPORTED;
   p.MT = mt;
+  p.SB = sb;
   p.tmem_cols = pow2_cols(mt * p.acc_stride);
   p.tiles_per_batch = (a->T + mt * 128 - 1) / (mt * 128);
   const long long gx = (long long)p.tiles_per_batch * a->B;

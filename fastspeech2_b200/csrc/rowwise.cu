@@ -290,44 +290,56 @@ int length_regulate(const fs2_length_regulate_args* a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ conv_post + tanh (hifigan/models.py:161-163)
-// C_in = 32, one output channel: 128 B per input row, HBM-bound.  One thread per output sample; neighbouring threads
-// share input rows through L1.
-__global__ void conv_post_kernel(const fs2_conv_post_args a) {
-  extern __shared__ float wsm[];  // [taps][C]
-  for (int i = threadIdx.x; i < a.taps * a.C; i += blockDim.x) wsm[i] = a.w[i];
-  __syncthreads();
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)a.B * a.T) return;
-  const int b = (int)(idx / a.T), t = (int)(idx - (long long)b * a.T);
-  const int pad = (a.taps - 1) / 2;
-  const int C4 = a.C / 4;
-  float acc = __ldg(a.bias);
-  for (int j = 0; j < a.taps; j++) {
-    const int ti = t + j - pad;
-    if (ti < 0 || ti >= a.T) continue;
-    const float4* xr = reinterpret_cast<const float4*>(a.x) + ((long long)b * a.T + ti) * C4;
-    const float* wj = wsm + j * a.C;
-    for (int c = 0; c < C4; c++) {
-      float4 v = __ldg(xr + c);
+// C_in = 32, one output channel: 128 B per input row, HBM-bound (algorithmic traffic = one read of x).  A CTA stages
+// 256 + taps - 1 activated rows in shared memory with fully coalesced float4 loads (row stride C+1 floats -> conflict-free
+// column walks), then each thread reduces its own output sample from shared memory.
+constexpr int CP_ROWS = 256;
+__global__ void __launch_bounds__(CP_ROWS) conv_post_kernel(const fs2_conv_post_args a, int tiles_per_batch) {
+  extern __shared__ float cp_smem[];
+  const int C = a.C, ld = C + 1, pad = (a.taps - 1) / 2;
+  float* wsm = cp_smem;                   // [taps][C]
+  float* xs = cp_smem + a.taps * C;       // [CP_ROWS + taps - 1][C + 1]
+  const int b = blockIdx.x / tiles_per_batch;
+  const int t0 = (blockIdx.x % tiles_per_batch) * CP_ROWS;
+  for (int i = threadIdx.x; i < a.taps * C; i += blockDim.x) wsm[i] = a.w[i];
+  const int rows = CP_ROWS + a.taps - 1, C4 = C / 4;
+  const float4* xb = reinterpret_cast<const float4*>(a.x) + (long long)b * a.T * C4;
+  for (int i = threadIdx.x; i < rows * C4; i += blockDim.x) {
+    const int r = i / C4, c4 = i - r * C4;
+    const int t = t0 - pad + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < a.T) {
+      v = __ldg(xb + (long long)t * C4 + c4);
       v.x = v.x > 0.f ? v.x : v.x * a.in_slope;
       v.y = v.y > 0.f ? v.y : v.y * a.in_slope;
       v.z = v.z > 0.f ? v.z : v.z * a.in_slope;
       v.w = v.w > 0.f ? v.w : v.w * a.in_slope;
-      acc = fmaf(v.x, wj[c * 4 + 0], acc);
-      acc = fmaf(v.y, wj[c * 4 + 1], acc);
-      acc = fmaf(v.z, wj[c * 4 + 2], acc);
-      acc = fmaf(v.w, wj[c * 4 + 3], acc);
     }
+    float* d = xs + r * ld + c4 * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
-  a.wav[idx] = tanhf(acc);
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= a.T) return;
+  float acc = __ldg(a.bias);
+  for (int j = 0; j < a.taps; j++) {
+    const float* xr = xs + (threadIdx.x + j) * ld;
+    const float* wj = wsm + j * C;
+#pragma unroll 8
+    for (int c = 0; c < C; c++) acc = fmaf(xr[c], wj[c], acc);
+  }
+  a.wav[(long long)b * a.T + t] = tanhf(acc);
 }
 
 int conv_post(const fs2_conv_post_args* a, cudaStream_t s) {
   if (!a || !a->x || !a->w || !a->bias || !a->wav || a->B <= 0 || a->T <= 0 || a->C <= 0 || a->taps <= 0) return FS2_ERR_ARG;
-  if (a->C % 4 || a->taps * a->C * 4 > 32768) return FS2_ERR_UNSUPPORTED;
+  const size_t smem = ((size_t)a->taps * a->C + (size_t)(CP_ROWS + a->taps - 1) * (a->C + 1)) * sizeof(float);
+  if (a->C % 4 || smem > 48 * 1024) return FS2_ERR_UNSUPPORTED;
+  const int tiles = (a->T + CP_ROWS - 1) / CP_ROWS;
   const long long n = (long long)a->B * a->T;
+  if ((long long)tiles * a->B > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   prof_before(s);
-  conv_post_kernel<<<(unsigned)((n + 255) / 256), 256, a->taps * a->C * sizeof(float), s>>>(*a);
+  conv_post_kernel<<<(unsigned)(tiles * a->B), CP_ROWS, smem, s>>>(*a, tiles);
   prof_after(s, 3, 2.0 * n * a->taps * a->C);
   FS2_LAUNCH_CHECK();
   return FS2_OK;

@@ -25,9 +25,11 @@ def lin_w(w: Tensor) -> Tensor:
 
 def conv_tc_block(n_out: int) -> int:
     """Output channels per CTA of the tcgen05 kernel (mirror of conv_tc_nb in csrc/conv_tc.cu); 0 = unsupported."""
-    if n_out <= 256:
-        return n_out if n_out % 16 == 0 else 0
-    for nb in range(256, 15, -16):
+    if n_out % 16:
+        return 0
+    if n_out <= 128:
+        return n_out
+    for nb in range(128, 15, -16):
         if n_out % nb == 0:
             return nb
     return 0
