@@ -30,7 +30,7 @@ struct ConvP {
   int tiles_per_batch;
 };
 
-template <int BN>
+template <int BN, int ACT>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
   constexpr int TN = BN / 16;              // 8, 4 or 2 columns per thread
   constexpr int NG = (TN == 8) ? 2 : 1;    // column groups per thread
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
 #pragma unroll
       for (int j = 0; j < GW; j++) {
         float u = acc[i][g * GW + j] + (p.bias ? __ldg(p.bias + nb + j) : 0.f);
-        u = apply_act(u, p.out_act, p.out_slope);
+        u = ACT == FS2_ACT_RELU ? fmaxf(u, 0.f) : ACT == FS2_ACT_TANH ? tanhf(u) : ACT == FS2_ACT_LRELU ? (u > 0.f ? u : u * p.out_slope) : u;
         if (rrow) u += rrow[nb + j];
         u *= p.alpha;
         if (p.accumulate) u += yrow[nb + j];
@@ -203,16 +203,24 @@ int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s) {
   const long long gx = (long long)p.tiles_per_batch * a->B;
   if (gx > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   prof_before(s);
+#define FS2_SIMT_LAUNCH(BN_, grid_)                                                                   \
+  switch (a->out_act) {                                                                               \
+    case FS2_ACT_RELU: conv_simt_kernel<BN_, FS2_ACT_RELU><<<grid_, 256, 0, s>>>(p); break;           \
+    case FS2_ACT_TANH: conv_simt_kernel<BN_, FS2_ACT_TANH><<<grid_, 256, 0, s>>>(p); break;           \
+    case FS2_ACT_LRELU: conv_simt_kernel<BN_, FS2_ACT_LRELU><<<grid_, 256, 0, s>>>(p); break;         \
+    default: conv_simt_kernel<BN_, FS2_ACT_NONE><<<grid_, 256, 0, s>>>(p); break;                     \
+  }
   if (a->N > 64) {
     dim3 grid((unsigned)gx, (a->N + 127) / 128);
-    conv_simt_kernel<128><<<grid, 256, 0, s>>>(p);
+    FS2_SIMT_LAUNCH(128, grid)
   } else if (a->N > 32) {
     dim3 grid((unsigned)gx, 1);
-    conv_simt_kernel<64><<<grid, 256, 0, s>>>(p);
+    FS2_SIMT_LAUNCH(64, grid)
   } else {
     dim3 grid((unsigned)gx, 1);
-    conv_simt_kernel<32><<<grid, 256, 0, s>>>(p);
+    FS2_SIMT_LAUNCH(32, grid)
   }
+#undef FS2_SIMT_LAUNCH
   prof_after(s, 0, 2.0 * a->B * a->T * (double)a->Cin * a->taps * a->N);
   FS2_LAUNCH_CHECK();
   return FS2_OK;

@@ -4,38 +4,42 @@
 //
 // Why 3xTF32: single-pass TF32 misses the parity bars (mel 1.2e-3 vs 1e-3, waveform 5.3e-4 vs 1e-4).
 // Each fp32 operand is split x = hi + lo with hi = x & 0xffffe000 (exactly a TF32 value) and lo = x - hi (exact in fp32);
-// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM leaves a relative error of ~2^-21 per product.
+// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM.
 //
-// Data movement per CTA (one utterance, MT consecutive 128-row time tiles, one block of N <= 256 output channels):
-//   * A (activations): 4 transform warps read the [MT*128 + (taps-1)*dil] x 16-channel slab of the current K-block ONCE from
-//     global (float4, coalesced), apply the input activation, split hi/lo and store both in the UMMA no-swizzle K-major
-//     layout  [16-byte K-chunk][row][4 floats].  In that layout a core matrix (8 rows x 16 B) starting at ANY row is 128
-//     contiguous bytes, so every conv tap is just a descriptor whose start address is advanced by tap*dil rows: the slab is
-//     loaded and split once per K-block, not once per tap.
-//   * B (weights): pre-split and pre-tiled on the host into the exact smem image of one (tap, K-block) stage
-//     ([hi|lo][K-chunk][n][4 floats]); one cp.async.bulk (TMA bulk engine) per stage, mbarrier complete_tx.
-//   * D: MT accumulators of 128 lanes x N fp32 columns in TMEM; each B stage feeds MT*2*3 MMAs (M=128, K=8).
-//   * Epilogue: the transform warps turn into epilogue warps: tcgen05.ld (thread == output row) -> bias / activation /
-//     residual / alpha / accumulate / pad-row mask -> 16-byte global stores.
-// Warp roles: warp 0 = weight-stage producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = transform then epilogue.
+// Persistent, warp-specialised kernel: one CTA per SM walks a list of work items (MT consecutive 128-row time tiles of
+// one utterance x one block of NB <= 128 output channels); four roles overlap through mbarrier rings:
+//   warp 0      weight producer: every (tap, 16-channel K-block) weight stage is ONE cp.async.bulk (TMA bulk engine) of a
+//               host-pre-split, host-pre-tiled smem image  [hi|lo][16-byte K-chunk][n][4 floats].
+//   warps 2-5   activation transform: read the [MT*128 + (taps-1)*dil] x 16-channel slab of a K-block ONCE from global
+//               (float4, one K-block of register prefetch), apply the input activation, split hi/lo and store both in the
+//               UMMA no-swizzle K-major layout [16-byte K-chunk][row][4 floats].  There a core matrix (8 rows x 16 B)
+//               starting at ANY row is 128 contiguous bytes, so each conv tap is just the same slab with the descriptor start
+//               address advanced by tap*dil rows: the slab is loaded and split once per K-block, not once per tap.
+//   warp 1      MMA issuer (one thread): per weight stage MT * 2 (K=8 steps) * 3 (split terms) tcgen05.mma, M=128, N=NB,
+//               accumulating into one of two TMEM accumulator sets; tcgen05.commit releases slab / weight stages and
+//               publishes the accumulators.
+//   warps 6-9   epilogue: tcgen05.ld (thread == output row) -> per-warp 32x36 smem transpose so that 8 lanes cover one
+//               row's 128 bytes -> bias / activation / residual / alpha / accumulate / pad-row mask -> full-line global I/O.
+//               Runs on work item i while the MMAs of item i+1 fill the other accumulator set.
 #include "common.cuh"
 
 namespace fs2 {
 
 constexpr int TC_KB = 16;          // input channels per K-block (two K=8 TF32 MMAs)
 constexpr int TC_CHUNKS = TC_KB / 4;
-constexpr int TC_SA = 2;           // activation slab stages
-constexpr int TC_SB_MAX = 4;       // weight stages (runtime: p.SB <= TC_SB_MAX)
-constexpr int TC_THREADS = 192;
-constexpr int TC_LD = 8;           // 16-byte global loads in flight per transform thread
+constexpr int TC_SA_MAX = 4;       // activation slab stages (runtime p.SA)
+constexpr int TC_SB_MAX = 8;       // weight stages (runtime p.SB)
+constexpr int TC_THREADS = 320;
+constexpr int TC_LD = 10;          // 16-byte global loads per transform thread per K-block (slabs of <= 320 rows)
+constexpr int TC_STAGE_FLOATS = 32 * 36;   // per-epilogue-warp transpose tile
 
 struct TcP {
   const float* x; long long xbs, xrs;
   int B, T, Cin;
-  const float* wt;                 // tiled weights, see pack_conv_tc()
+  const float* wt;                 // tiled weights, see packing.pack_conv_tc
   const float* bias;
   int N;                           // total output channels
-  int NB;                          // output channels per CTA (MMA N), N % NB == 0, NB % 16 == 0, NB <= 256
+  int NB;                          // output channels per work item (MMA N), N % NB == 0, NB % 16 == 0, NB <= 128
   int taps, dil, pad;
   int in_act; float in_slope;
   int out_act; float out_slope;
@@ -43,13 +47,14 @@ struct TcP {
   float alpha; int accumulate;
   const int* row_lens;
   float* y; long long ybs, yrs;
-  int MT;                          // 128-row tiles per CTA
-  int SB;                          // weight stages in flight
+  int MT;                          // 128-row tiles per work item
+  int TG;                          // accumulators per tile: 1 = all split terms together, 2 = {hi*hi | cross}, 3 = one each
+  int SA, SB;                      // ring depths
   int R;                           // slab rows held in smem (>= MT*128 + (taps-1)*dil, R % 8 == 2)
-  int tiles_per_batch;
+  int tiles_per_batch;             // work items per utterance
+  int n_items;                     // total work items = (N/NB) * B * tiles_per_batch
   int acc_stride;                  // TMEM columns between accumulators
-  int tmem_cols;                   // power of two >= MT*acc_stride
-  unsigned variant;                // debug: bit0 swaps LBO/SBO
+  int tmem_cols;                   // power of two >= 2*MT*TG*acc_stride
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -94,7 +99,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
@@ -102,7 +107,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -131,31 +135,137 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcP p) {
+struct Item { int nblk, b, t0; };
+__device__ __forceinline__ Item decode_item(const TcP& p, int item) {
+  const int per_blk = p.B * p.tiles_per_batch;
+  Item it;
+  it.nblk = item / per_blk;
+  const int rem = item - it.nblk * per_blk;
+  it.b = rem / p.tiles_per_batch;
+  it.t0 = (rem - it.b * p.tiles_per_batch) * p.MT * 128;
+  return it;
+}
+
+template <int ACT>
+__device__ __forceinline__ float tc_act(float v, float slope) {
+  if (ACT == FS2_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == FS2_ACT_TANH) return tanhf(v);
+  if (ACT == FS2_ACT_LRELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+// One 32-row x W-column block of one accumulator: TMEM -> regs -> smem transpose -> coalesced global I/O.
+// W = 32: 8 lanes per row, 4 rows per pass, 8 passes.  W = 16: 4 lanes per row, 8 rows per pass, 4 passes.
+template <int ACT, int W, bool FULL>
+__device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, float* stage, int lane, float* yptr, const float* rptr,
+                                                  const float* bias, int rows_live, int rows_valid) {
+  constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+  {
+    uint32_t v[32];
+    if (W == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
+    for (int g = 1; g < p.TG; g++) {                   // split-term accumulators are summed here, in fp32 round-to-nearest
+      uint32_t u[32];
+      if (W == 32) tc_ld32(taddr + g * p.acc_stride, u); else tc_ld16(taddr + g * p.acc_stride, u);
+#pragma unroll
+      for (int j = 0; j < W; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < W / 4; j++)
+      *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =
+          make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]), __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
+  }
+  __syncwarp();
+  const int rr = lane / LPR;
+  const float slope = p.out_slope, alpha = p.alpha;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias));
+  const long long ystep = (long long)RPI * p.yrs, rstep = (long long)RPI * p.rrs;
+  float4 rv[ITERS], yv[ITERS];
+#pragma unroll
+  for (int k = 0; k < ITERS; k++) {
+    rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    yv[k] = rv[k];
+  }
+  if (rptr) {
+#pragma unroll
+    for (int k = 0; k < ITERS; k++)
+      if (FULL || k * RPI + rr < rows_valid) rv[k] = *reinterpret_cast<const float4*>(rptr + k * rstep);
+  }
+  if (p.accumulate) {
+#pragma unroll
+    for (int k = 0; k < ITERS; k++)
+      if (FULL || k * RPI + rr < rows_valid) yv[k] = *reinterpret_cast<const float4*>(yptr + k * ystep);
+  }
+#pragma unroll
+  for (int k = 0; k < ITERS; k++) {
+    const int r = k * RPI + rr;
+    if (FULL || r < rows_valid) {
+      const float4 a = *reinterpret_cast<const float4*>(stage + r * 36 + (lane % LPR) * 4);
+      float4 o;
+      o.x = (tc_act<ACT>(a.x + bv.x, slope) + rv[k].x) * alpha + yv[k].x;
+      o.y = (tc_act<ACT>(a.y + bv.y, slope) + rv[k].y) * alpha + yv[k].y;
+      o.z = (tc_act<ACT>(a.z + bv.z, slope) + rv[k].z) * alpha + yv[k].z;
+      o.w = (tc_act<ACT>(a.w + bv.w, slope) + rv[k].w) * alpha + yv[k].w;
+      if (!FULL && r >= rows_live) o = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(yptr + k * ystep) = o;
+    }
+  }
+  __syncwarp();   // the staging tile is rewritten by the next block
+}
+
+template <int ACT>
+__device__ __forceinline__ void tc_epilogue_item(const TcP& p, uint32_t tmem_acc, float* stage, int q, int lane, const Item& it) {
+  const int NB = p.NB, n0 = it.nblk * NB;
+  const int len_b = p.row_lens ? min(p.row_lens[it.b], p.T) : p.T;
+  for (int mt = 0; mt < p.MT; mt++) {
+    const int row0 = it.t0 + mt * 128 + q * 32;
+    const int rows_valid = min(32, p.T - row0);        // rows that exist
+    if (rows_valid <= 0) continue;                     // warp-uniform
+    const int rows_live = min(32, len_b - row0);       // rows that are not padding (may be <= 0)
+    const bool full = rows_valid == 32 && rows_live == 32;
+    const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.TG * p.acc_stride);
+    for (int c = 0; c < NB; c += 32) {
+      const int w = (NB - c) >= 32 ? 32 : 16;          // NB % 16 == 0
+      const int lpr = w >> 2;
+      const int rr = lane / lpr, cc = (lane % lpr) * 4;
+      float* yptr = p.y + (long long)it.b * p.ybs + (long long)(row0 + rr) * p.yrs + n0 + c + cc;
+      const float* rptr = p.res ? p.res + (long long)it.b * p.rbs + (long long)(row0 + rr) * p.rrs + n0 + c + cc : nullptr;
+      const float* bias = p.bias ? p.bias + n0 + c + cc : nullptr;
+      if (w == 32) {
+        if (full) tc_epilogue_block<ACT, 32, true>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid);
+        else tc_epilogue_block<ACT, 32, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid);
+      } else {
+        tc_epilogue_block<ACT, 16, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid);
+      }
+    }
+  }
+}
+
+template <int MT, int TG>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int R = p.R, NB = p.NB;
+  const int R = p.R, NB = p.NB, SA = p.SA, SB = p.SB;
   const uint32_t a_plane = (uint32_t)TC_CHUNKS * R * 16;          // bytes of one hi (or lo) slab
   const uint32_t b_plane = (uint32_t)TC_CHUNKS * NB * 16;         // bytes of one hi (or lo) weight tile
-  unsigned char* a_base = smem_raw;                                // [SA][hi|lo][chunk][R][16 B]
-  unsigned char* b_base = a_base + (size_t)TC_SA * 2 * a_plane;    // [SB][hi|lo][chunk][NB][16 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.SB * 2 * b_plane);
-  uint64_t* fullA = bars;                // [SA]
-  uint64_t* emptyA = bars + TC_SA;       // [SA]
-  uint64_t* fullB = emptyA + TC_SA;      // [SB_MAX]
-  uint64_t* emptyB = fullB + TC_SB_MAX;  // [SB_MAX]
-  uint64_t* accFull = emptyB + TC_SB_MAX;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accFull + 1);
+  float* stage_all = reinterpret_cast<float*>(smem_raw);           // [4 warps][32 x 36] epilogue transpose tiles
+  unsigned char* a_base = smem_raw + 4 * TC_STAGE_FLOATS * sizeof(float);   // [SA][hi|lo][chunk][R][16 B]
+  unsigned char* b_base = a_base + (size_t)SA * 2 * a_plane;       // [SB][hi|lo][chunk][NB][16 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)SB * 2 * b_plane);
+  uint64_t* fullA = bars;                  // [SA_MAX]
+  uint64_t* emptyA = fullA + TC_SA_MAX;    // [SA_MAX]
+  uint64_t* fullB = emptyA + TC_SA_MAX;    // [SB_MAX]
+  uint64_t* emptyB = fullB + TC_SB_MAX;    // [SB_MAX]
+  uint64_t* accFull = emptyB + TC_SB_MAX;  // [2]
+  uint64_t* accEmpty = accFull + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
 
-  const int b = blockIdx.x / p.tiles_per_batch;
-  const int t0 = (blockIdx.x % p.tiles_per_batch) * p.MT * 128;
-  const int nblk = blockIdx.y;
   const int KBLOCKS = p.Cin / TC_KB;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < TC_SA; i++) { mbar_init(&fullA[i], 128); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < TC_SA_MAX; i++) { mbar_init(&fullA[i], 128); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < TC_SB_MAX; i++) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    mbar_init(accFull, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(&accFull[i], 1); mbar_init(&accEmpty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -166,177 +276,161 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcP p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t acc_set = (uint32_t)(MT * TG * p.acc_stride);      // columns per accumulator set
 
   if (warp == 0) {
     // ===================== weight-stage producer (TMA bulk copies) =====================
     if (lane == 0) {
       const uint32_t stage_bytes = 2 * b_plane;
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
-      int it = 0;
-      for (int kb = 0; kb < KBLOCKS; kb++) {
-        for (int tap = 0; tap < p.taps; tap++, it++) {
-          const int s = it % p.SB;
-          const uint32_t ph = (it / p.SB) & 1;
-          mbar_wait(&emptyB[s], ph ^ 1);
-          mbar_expect_tx(&fullB[s], stage_bytes);
-          bulk_g2s(b_base + (size_t)s * stage_bytes, wsrc + ((size_t)tap * KBLOCKS + kb) * stage_bytes, stage_bytes, &fullB[s]);
+      uint32_t itB = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int nblk = item / (p.B * p.tiles_per_batch);
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
+        for (int kb = 0; kb < KBLOCKS; kb++) {
+          for (int tap = 0; tap < p.taps; tap++, itB++) {
+            const uint32_t s = itB % SB;
+            mbar_wait(&emptyB[s], ((itB / SB) & 1) ^ 1);
+            mbar_expect_tx(&fullB[s], stage_bytes);
+            bulk_g2s(b_base + (size_t)s * stage_bytes, wsrc + ((size_t)tap * KBLOCKS + kb) * stage_bytes, stage_bytes, &fullB[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(NB);
-      // descriptors differ only in the 14-bit start-address field (16-byte units): build the constant part once and add offsets
-      const uint64_t a_const = umma_desc(0, (uint32_t)R * 16, 128), b_const = umma_desc(0, (uint32_t)NB * 16, 128);
-      const uint32_t a_kk = 2u * (uint32_t)R, b_kk = 2u * (uint32_t)NB;     // two 16-byte K-chunks per K=8 MMA, in 16-byte units
-      int it = 0;
-      for (int kb = 0; kb < KBLOCKS; kb++) {
-        const int sa = kb % TC_SA;
-        mbar_wait(&fullA[sa], (kb / TC_SA) & 1);
+    // The whole warp runs the (warp-uniform) loops and barrier waits so that descriptors live in uniform registers; one
+    // elected lane issues the MMAs and the commits.  Per weight stage the 6*MT MMAs are fully unrolled and every operand is
+    // a precomputed base plus a constant: the issue cost per MMA must stay well below the 16..64 cycles an MMA occupies
+    // the tensor pipe (a generic address computation per MMA was measured to be the bottleneck).
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    const uint32_t idesc = umma_idesc_tf32(NB);
+    const uint64_t a_const = umma_desc(0, (uint32_t)R * 16, 128), b_const = umma_desc(0, (uint32_t)NB * 16, 128);
+    const uint32_t a_kk = 2u * (uint32_t)R, b_kk = 2u * (uint32_t)NB;       // two 16-byte K-chunks per K=8 MMA, in 16-byte units
+    const uint32_t tile_cols = (uint32_t)(TG * p.acc_stride);
+    const uint32_t g_cross = TG >= 2 ? (uint32_t)p.acc_stride : 0u;            // lo*hi (and hi*lo when TG == 2)
+    const uint32_t g_cross2 = TG == 3 ? 2u * (uint32_t)p.acc_stride : g_cross;  // hi*lo
+    uint32_t itA = 0, itB = 0, itT = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++) {
+      const uint32_t buf = itT & 1;
+      mbar_wait(&accEmpty[buf], ((itT >> 1) & 1) ^ 1);            // epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t d0 = tmem + buf * acc_set;
+      for (int kb = 0; kb < KBLOCKS; kb++, itA++) {
+        const uint32_t sa = itA % SA;
+        mbar_wait(&fullA[sa], (itA / SA) & 1);
         tc_fence_after();
         const uint64_t a_hi = a_const | (uint64_t)(smem_u32(a_base + (size_t)sa * 2 * a_plane) >> 4);
         const uint64_t a_lo = a_hi + (a_plane >> 4);
-        for (int tap = 0; tap < p.taps; tap++, it++) {
-          const int sb = it % p.SB;
-          mbar_wait(&fullB[sb], (it / p.SB) & 1);
+        for (int tap = 0; tap < p.taps; tap++, itB++) {
+          const uint32_t sb = itB % SB;
+          mbar_wait(&fullB[sb], (itB / SB) & 1);
           tc_fence_after();
-          const uint64_t b_hi = b_const | (uint64_t)(smem_u32(b_base + (size_t)sb * 2 * b_plane) >> 4);
-          const uint64_t b_lo = b_hi + (b_plane >> 4);
-          uint32_t row = (uint32_t)(tap * p.dil);
-          uint32_t d = tmem;
-          for (int mt = 0; mt < p.MT; mt++, row += 128, d += (uint32_t)p.acc_stride) {
+          if (leader) {
+            const uint64_t b_hi = b_const | (uint64_t)(smem_u32(b_base + (size_t)sb * 2 * b_plane) >> 4);
+            const uint64_t b_lo = b_hi + (b_plane >> 4);
+            const uint64_t ah0 = a_hi + (uint32_t)(tap * p.dil), al0 = a_lo + (uint32_t)(tap * p.dil);
+            const uint32_t first = (kb | tap) ? 1u : 0u;
+            // consecutive MMAs alternate between tiles / accumulator groups
 #pragma unroll
             for (int kk = 0; kk < TC_KB / 8; kk++) {
-              const uint64_t ah = a_hi + row + kk * a_kk, al = a_lo + row + kk * a_kk;
+              const uint32_t acc_kk = (first | (uint32_t)kk) ? 1u : 0u;
               const uint64_t bh = b_hi + kk * b_kk, bl = b_lo + kk * b_kk;
-              tc_mma_tf32(d, al, bh, idesc, (kb | tap | kk) ? 1u : 0u);   // small terms first
-              tc_mma_tf32(d, ah, bl, idesc, 1u);
-              tc_mma_tf32(d, ah, bh, idesc, 1u);
+#pragma unroll
+              for (int mt = 0; mt < MT; mt++)          // A_lo * B_hi
+                tc_mma_tf32(d0 + mt * tile_cols + g_cross, al0 + mt * 128 + kk * a_kk, bh, idesc, acc_kk);
+#pragma unroll
+              for (int mt = 0; mt < MT; mt++)          // A_hi * B_hi
+                tc_mma_tf32(d0 + mt * tile_cols, ah0 + mt * 128 + kk * a_kk, bh, idesc, TG >= 2 ? acc_kk : 1u);
+#pragma unroll
+              for (int mt = 0; mt < MT; mt++)          // A_hi * B_lo
+                tc_mma_tf32(d0 + mt * tile_cols + g_cross2, ah0 + mt * 128 + kk * a_kk, bl, idesc, TG == 3 ? acc_kk : 1u);
             }
+            tc_commit(&emptyB[sb]);                    // weight stage free once these MMAs retire
           }
-          tc_commit(&emptyB[sb]);                      // weight stage free once these MMAs retire
+          __syncwarp();
         }
-        tc_commit(&emptyA[sa]);                        // slab free
+        if (leader) tc_commit(&emptyA[sa]);            // slab stage free
+        __syncwarp();
       }
-      tc_commit(accFull);
+      if (leader) tc_commit(&accFull[buf]);            // accumulators of this work item complete
+      __syncwarp();
     }
-  } else {
-    // ===================== transform warps (activation + hi/lo split), then epilogue =====================
+  } else if (warp < 6) {
+    // ===================== transform warps (activation + hi/lo split) =====================
     const int wt = tid - 64;                           // 0..127
-    const float* xb = p.x + (long long)b * p.xbs;
-    const int rows_needed = p.MT * 128 + (p.taps - 1) * p.dil;
+    const int rows_needed = MT * 128 + (p.taps - 1) * p.dil;
     const int items = rows_needed * TC_CHUNKS;
-    const int t_first = t0 - p.pad;
-    for (int kb = 0; kb < KBLOCKS; kb++) {
-      const int sa = kb % TC_SA;
-      mbar_wait(&emptyA[sa], ((kb / TC_SA) & 1) ^ 1);
+    // One K-block of register prefetch: the loads of the next K-block (possibly of the next work item) are issued right
+    // after the current one has been stored, so their latency is spent while waiting for the slab stage to be released.
+    float4 v[TC_LD];
+    auto issue_loads = [&](int item, int kb) {
+      const Item it = decode_item(p, item);
+      const float* xb = p.x + (long long)it.b * p.xbs + kb * TC_KB;
+      const int t_first = it.t0 - p.pad;
+#pragma unroll
+      for (int u = 0; u < TC_LD; u++) {
+        const int idx = u * 128 + wt;
+        const int row = idx >> 2, ch = idx & 3;
+        const int t = t_first + row;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < items && t >= 0 && t < p.T) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * p.xrs + ch * 4));
+      }
+    };
+    int item = blockIdx.x, kb = 0;
+    if (item < p.n_items) issue_loads(item, 0);
+    uint32_t itA = 0;
+    const bool lrelu_in = p.in_act == FS2_ACT_LRELU;
+    const float in_slope = p.in_slope;
+    while (item < p.n_items) {
+      const uint32_t sa = itA % SA;
+      mbar_wait(&emptyA[sa], ((itA / SA) & 1) ^ 1);
       unsigned char* hi = a_base + (size_t)sa * 2 * a_plane;
       unsigned char* lo = hi + a_plane;
-      const int c0 = kb * TC_KB;
-      for (int base = 0; base < items; base += 128 * TC_LD) {
-        float4 v[TC_LD];
 #pragma unroll
-        for (int u = 0; u < TC_LD; u++) {              // TC_LD independent 16-byte loads in flight per thread
-          const int idx = base + u * 128 + wt;
-          const int row = idx >> 2, ch = idx & 3;
-          const int t = t_first + row;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < items && t >= 0 && t < p.T) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * p.xrs + c0 + ch * 4));
+      for (int u = 0; u < TC_LD; u++) {
+        const int idx = u * 128 + wt;
+        if (idx >= items) continue;
+        const int row = idx >> 2, ch = idx & 3;
+        float4 a = v[u];
+        if (lrelu_in) {
+          a.x = a.x > 0.f ? a.x : a.x * in_slope; a.y = a.y > 0.f ? a.y : a.y * in_slope;
+          a.z = a.z > 0.f ? a.z : a.z * in_slope; a.w = a.w > 0.f ? a.w : a.w * in_slope;
         }
-#pragma unroll
-        for (int u = 0; u < TC_LD; u++) {
-          const int idx = base + u * 128 + wt;
-          if (idx >= items) continue;
-          const int row = idx >> 2, ch = idx & 3;
-          float4 a = v[u];
-          if (p.in_act == FS2_ACT_LRELU) {
-            a.x = a.x > 0.f ? a.x : a.x * p.in_slope; a.y = a.y > 0.f ? a.y : a.y * p.in_slope;
-            a.z = a.z > 0.f ? a.z : a.z * p.in_slope; a.w = a.w > 0.f ? a.w : a.w * p.in_slope;
-          }
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u); l.x = a.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u); l.y = a.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u); l.z = a.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u); l.w = a.w - h.w;
-          const size_t off = ((size_t)ch * R + row) * 16;
-          *reinterpret_cast<float4*>(hi + off) = h;
-          *reinterpret_cast<float4*>(lo + off) = l;
-        }
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u); l.x = a.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u); l.y = a.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u); l.z = a.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u); l.w = a.w - h.w;
+        const uint32_t off = ((uint32_t)ch * R + row) * 16;
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = l;
       }
       fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&fullA[sa]);
+      itA++;
+      if (++kb == KBLOCKS) { kb = 0; item += gridDim.x; }
+      if (item < p.n_items) issue_loads(item, kb);
     }
-
-    // ---- epilogue: TMEM -> registers -> (per-warp smem transpose) -> coalesced global I/O ----
-    // tcgen05.ld hands each thread one output ROW; writing rows straight out would touch 32 different 128-byte lines per
-    // instruction.  Each warp therefore transposes its 32 x 32 block through a private 32 x 36 float staging tile (the slab
-    // buffers are free once accFull has fired) so that 8 lanes cover one row's 128 bytes: every global load (residual,
-    // accumulate) and store is a full-line access.
-    mbar_wait(accFull, 0);
-    tc_fence_after();
+  } else {
+    // ===================== epilogue warps =====================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const int len_b = p.row_lens ? p.row_lens[b] : p.T;
-    const int n0 = nblk * NB;
-    float* stage = reinterpret_cast<float*>(a_base) + (warp - 2) * (32 * 36);
-    for (int mt = 0; mt < p.MT; mt++) {
-      const int row_base = t0 + mt * 128 + q * 32;
-      for (int c = 0; c < NB; c += 32) {
-        const int w = (NB - c) >= 32 ? 32 : 16;        // NB % 16 == 0
-        {
-          uint32_t v[32];
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.acc_stride + c);
-          if (w == 32) {
-            tc_ld32(taddr, v);
-          } else {
-            uint32_t v16[16];
-            tc_ld16(taddr, v16);
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = v16[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            if (j * 4 < w)
-              *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =
-                  make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]), __uint_as_float(v[j * 4 + 2]),
-                              __uint_as_float(v[j * 4 + 3]));
-        }
-        __syncwarp();
-        const int lpr = w >> 2;                        // lanes per row (8 or 4)
-        const int rpi = 32 / lpr;                      // rows per iteration (4 or 8)
-        const int iters = 32 / rpi;                    // 8 or 4
-        const int rr = lane / lpr, cc = (lane % lpr) * 4;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cc));
-        float4 rv[8], yv[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {                  // all global loads of this block in flight before any store
-          rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          yv[k] = rv[k];
-          const int t = row_base + k * rpi + rr;
-          if (k < iters && t < p.T) {
-            const long long off = (long long)t;
-            if (p.res) rv[k] = *reinterpret_cast<const float4*>(p.res + (long long)b * p.rbs + off * p.rrs + n0 + c + cc);
-            if (p.accumulate) yv[k] = *reinterpret_cast<const float4*>(p.y + (long long)b * p.ybs + off * p.yrs + n0 + c + cc);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int r = k * rpi + rr;
-          const int t = row_base + r;
-          if (k < iters && t < p.T) {
-            const float4 a = *reinterpret_cast<const float4*>(stage + r * 36 + cc);
-            float4 o;
-            o.x = (apply_act(a.x + bv.x, p.out_act, p.out_slope) + rv[k].x) * p.alpha + yv[k].x;
-            o.y = (apply_act(a.y + bv.y, p.out_act, p.out_slope) + rv[k].y) * p.alpha + yv[k].y;
-            o.z = (apply_act(a.z + bv.z, p.out_act, p.out_slope) + rv[k].z) * p.alpha + yv[k].z;
-            o.w = (apply_act(a.w + bv.w, p.out_act, p.out_slope) + rv[k].w) * p.alpha + yv[k].w;
-            if (t >= len_b) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(p.y + (long long)b * p.ybs + (long long)t * p.yrs + n0 + c + cc) = o;
-          }
-        }
-        __syncwarp();                                  // staging tile is rewritten by the next block
+    float* stage = stage_all + (warp - 6) * TC_STAGE_FLOATS;
+    uint32_t itT = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++) {
+      const uint32_t buf = itT & 1;
+      const Item it = decode_item(p, item);
+      mbar_wait(&accFull[buf], (itT >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * acc_set;
+      switch (p.out_act) {                             // uniform branch: keeps tanhf out of the other variants' inner loops
+        case FS2_ACT_RELU: tc_epilogue_item<FS2_ACT_RELU>(p, acc, stage, q, lane, it); break;
+        case FS2_ACT_TANH: tc_epilogue_item<FS2_ACT_TANH>(p, acc, stage, q, lane, it); break;
+        case FS2_ACT_LRELU: tc_epilogue_item<FS2_ACT_LRELU>(p, acc, stage, q, lane, it); break;
+        default: tc_epilogue_item<FS2_ACT_NONE>(p, acc, stage, q, lane, it); break;
       }
+      tc_fence_before();
+      mbar_arrive(&accEmpty[buf]);                     // all of this thread's tcgen05.ld of the set have completed
     }
   }
 
@@ -349,13 +443,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcP p) {
 }
 
 // ------------------------------------------------------------------ host side
+long long* g_tc_trace = nullptr;  // debug hook kept for ABI stability (unused by the persistent kernel)
+
 static int pow2_cols(int c) {
   int v = 32;
   while (v < c) v <<= 1;
   return v;
 }
 
-int conv_tc_nb(int N) {  // output channels per CTA: at most 128 so that two CTAs (256 TMEM columns each) share an SM
+int conv_tc_nb(int N) {  // output channels per work item: NB <= 128 keeps two accumulator sets of MT=2 tiles inside TMEM
   if (N % 16) return 0;
   if (N <= 128) return N;
   for (int nb = 128; nb >= 16; nb -= 16)
@@ -368,16 +464,32 @@ bool conv_tc_supported(const fs2_conv1d_args* a) {
   if ((a->x_row_stride & 3) || (a->x_batch_stride & 3) || (a->y_row_stride & 3) || (a->y_batch_stride & 3)) return false;
   if (a->res && ((a->res_row_stride & 3) || (a->res_batch_stride & 3))) return false;
   if (a->in_act != FS2_ACT_NONE && a->in_act != FS2_ACT_LRELU) return false;
-  if ((a->taps - 1) * a->dilation > 160) return false;
+  if ((a->taps - 1) * a->dilation > TC_LD * 32 - 128) return false;
   return true;
 }
 
+static int g_num_sms = 0;
+
 // `wt` must be the tiled layout produced by fastspeech2_b200.packing.pack_conv_tc (see fs2b200.h)
 int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s) {
+  (void)variant;
   if (!a || !a->x || !wt || !a->y) return FS2_ERR_ARG;
   if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
   if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
   if (!aligned16(a->x) || !aligned16(wt) || !aligned16(a->y) || (a->res && !aligned16(a->res))) return FS2_ERR_ARG;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const int mx = 227 * 1024;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e != cudaSuccess) { g_num_sms = 0; return FS2_ERR_CUDA - (int)e; }
+  }
   TcP p;
   p.x = a->x; p.xbs = a->x_batch_stride; p.xrs = a->x_row_stride;
   p.B = a->B; p.T = a->T; p.Cin = a->Cin;
@@ -387,54 +499,42 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.res = a->res; p.rbs = a->res_batch_stride; p.rrs = a->res_row_stride;
   p.alpha = a->alpha; p.accumulate = a->accumulate; p.row_lens = a->row_lens;
   p.y = a->y; p.ybs = a->y_batch_stride; p.yrs = a->y_row_stride;
-  p.variant = variant;
   p.acc_stride = (p.NB + 31) & ~31;
   const int halo = (a->taps - 1) * a->dilation;
   const int tiles128 = (a->T + 127) / 128;
-  // Two CTAs per SM (one's epilogue / slab load overlaps the other's MMAs): aim for <= ~112 KB of shared memory and <= 256
-  // TMEM columns per CTA; fall back to one CTA per SM when the halo makes the slab too large.
-  const size_t bar_bytes = (2 * TC_SA + 2 * TC_SB_MAX + 1) * 8 + 16;
-  const size_t budget2 = 112 * 1024, budget1 = 226 * 1024;
-  int mt = 256 / p.acc_stride;
-  if (mt > 2) mt = 2;
+  int mt = 2;                                          // two accumulator sets of MT tiles: 2*MT*acc_stride <= 512 columns
   if (mt > tiles128) mt = tiles128;
-  if (mt < 1) mt = 1;
-  size_t smem = 0;
-  int sb = 0;
-  for (;; mt--) {
-    int R = mt * 128 + halo;
-    R += (10 - (R & 7)) & 7;                           // R % 8 == 2: conflict-free transform stores
-    p.R = R;
-    const size_t a_bytes = (size_t)TC_SA * 2 * TC_CHUNKS * R * 16, b_stage = (size_t)2 * TC_CHUNKS * p.NB * 16;
-    for (sb = TC_SB_MAX; sb >= 2; sb--) {
-      smem = a_bytes + sb * b_stage + bar_bytes;
-      if (smem <= budget2) break;
-    }
-    if (sb >= 2) break;
-    if (mt == 1) {                                     // cannot fit two per SM: take what one CTA can have
-      for (sb = TC_SB_MAX; sb >= 2; sb--) {
-        smem = a_bytes + sb * b_stage + bar_bytes;
-        if (smem <= budget1) break;
-      }
-      if (sb < 2) return FS2_ERR_UNSUPPORTED;
-      break;
-    }
-  }
-  p.MT = mt;
-  p.SB = sb;
-  p.tmem_cols = pow2_cols(mt * p.acc_stride);
+  if (mt * 128 + halo > TC_LD * 32) mt = 1;            // the transform holds one slab K-block in registers
+  int R = mt * 128 + halo;
+  R += (10 - (R & 7)) & 7;                             // R % 8 == 2: conflict-free transform stores
+  p.MT = mt; p.R = R;
+  p.TG = p.acc_stride <= 32 ? 3 : (p.acc_stride <= 64 ? 2 : 1);   // spread split terms while two sets still fit in 512 columns
+  const size_t fixed = 4 * TC_STAGE_FLOATS * sizeof(float) + (2 * TC_SA_MAX + 2 * TC_SB_MAX + 4) * 8 + 16;
+  const size_t a_stage = (size_t)2 * TC_CHUNKS * R * 16, b_stage = (size_t)2 * TC_CHUNKS * p.NB * 16;
+  const size_t budget = 226 * 1024;
+  const int kblocks = a->Cin / TC_KB;
+  int sa = kblocks < 3 ? 2 : 3, sb = TC_SB_MAX;        // prefer deep weight rings (bulk-copy latency), then a third slab stage
+  while (fixed + sa * a_stage + sb * b_stage > budget && sb > 3) sb--;
+  while (fixed + sa * a_stage + sb * b_stage > budget && sa > 2) sa--;
+  while (fixed + sa * a_stage + sb * b_stage > budget && sb > 2) sb--;
+  if (fixed + sa * a_stage + sb * b_stage > budget) return FS2_ERR_UNSUPPORTED;
+  if (sa < TC_SA_MAX && kblocks >= 4 && fixed + (sa + 1) * a_stage + sb * b_stage <= budget) sa++;
+  p.SA = sa; p.SB = sb;
+  const size_t smem = fixed + sa * a_stage + sb * b_stage;
+  p.tmem_cols = pow2_cols(2 * mt * p.TG * p.acc_stride);
   p.tiles_per_batch = (a->T + mt * 128 - 1) / (mt * 128);
-  const long long gx = (long long)p.tiles_per_batch * a->B;
-  if (gx > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return FS2_ERR_CUDA - (int)e;
-    attr_set = true;
-  }
-  dim3 grid((unsigned)gx, a->N / p.NB);
+  const long long n_items = (long long)(a->N / p.NB) * a->B * p.tiles_per_batch;
+  if (n_items > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
+  p.n_items = (int)n_items;
+  const int grid = n_items < g_num_sms ? (int)n_items : g_num_sms;
   prof_before(s);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
+#define FS2_TC_LAUNCH(MT_, TG_) conv_tc_kernel<MT_, TG_><<<grid, TC_THREADS, smem, s>>>(p)
+  if (mt == 2) {
+    if (p.TG == 3) FS2_TC_LAUNCH(2, 3); else if (p.TG == 2) FS2_TC_LAUNCH(2, 2); else FS2_TC_LAUNCH(2, 1);
+  } else {
+    if (p.TG == 3) FS2_TC_LAUNCH(1, 3); else if (p.TG == 2) FS2_TC_LAUNCH(1, 2); else FS2_TC_LAUNCH(1, 1);
+  }
+#undef FS2_TC_LAUNCH
   prof_after(s, 0, 2.0 * a->B * a->T * (double)a->Cin * a->taps * a->N);
   FS2_LAUNCH_CHECK();
   return FS2_OK;

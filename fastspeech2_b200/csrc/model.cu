@@ -33,6 +33,7 @@ int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s);
 int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s);
 bool conv_tc_supported(const fs2_conv1d_args* a);
 int conv_tc_nb(int N);
+extern long long* g_tc_trace;
 
 // backend dispatch of the fs2_conv1d contract
 static int conv1d_dispatch(const fs2_conv1d_args* a, cudaStream_t s) {
@@ -303,6 +304,8 @@ size_t fs2_struct_size(int which) {
     default: return 0;
   }
 }
+/* debug only (not in the public header): per-CTA phase timestamps of the next tcgen05 conv launches */
+void fs2_debug_set_tc_trace(long long* buf) { g_tc_trace = buf; }
 int fs2_profile_begin(void) {
   g_prof.clear();
   g_prof_on = true;
