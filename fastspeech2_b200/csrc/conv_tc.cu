@@ -1,36 +1,45 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM Conv1d over channels-last activations, error-compensated 3xTF32.
+// tcgen05 (5th-gen tensor core) implicit-GEMM Conv1d over channels-last activations, error-compensated split-FP16.
 //
 //   y[b,t,n] = epilogue( sum_{tap} sum_c act(x[b, t + tap*dil - pad, c]) * w[tap][c][n] )        (contract: fs2_conv1d)
 //
-// Why 3xTF32: single-pass TF32 misses the parity bars (mel 1.2e-3 vs 1e-3, waveform 5.3e-4 vs 1e-4).
-// Each fp32 operand is split x = hi + lo with hi = x & 0xffffe000 (exactly a TF32 value) and lo = x - hi (exact in fp32);
-// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM.
+// Why a split: single-pass TF32 / FP16 / BF16 operands miss the parity bars (mel 1.2e-3 vs 1e-3, waveform 5.3e-4 vs 1e-4,
+// SURVEY.md section 7).  Each fp32 operand is split x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (x - hi is exact in
+// fp32): 22 significant bits, the same as a TF32 hi/lo split, but kind::f16 MMAs have K = 16 per instruction -- twice the
+// FLOPs per instruction and per shared-memory byte of kind::tf32.  D += A_lo*B_hi + A_hi*B_hi + A_hi*B_lo, fp32 accumulate in
+// TMEM.  Weights are pre-scaled by a per-layer power of two (kept in a 128-byte header of the tiled buffer) so that their lo
+// parts stay in fp16's normal range; activations are used unscaled (|x| <= 65504 clamp; a lo part below 2^-14 only costs an
+// ABSOLUTE error < 3e-8).  Emulated end to end on the CPU (exact accumulation) this split is as accurate as fp32 convolution
+// on both the synthetic and the shipped HiFi-GAN checkpoint; on the GPU the tensor core's round-toward-zero accumulator is
+// what remains (profiles/r01_tc_accumulate_bias.txt), and K = 16 halves the number of accumulation steps.
 //
 // Persistent, warp-specialised kernel: one CTA per SM walks a list of work items (MT consecutive 128-row time tiles of
 // one utterance x one block of NB <= 128 output channels); four roles overlap through mbarrier rings:
 //   warp 0      weight producer: every (tap, 16-channel K-block) weight stage is ONE cp.async.bulk (TMA bulk engine) of a
-//               host-pre-split, host-pre-tiled smem image  [hi|lo][16-byte K-chunk][n][4 floats].
+//               host-pre-split, host-pre-tiled smem image  [hi|lo][16-byte K-chunk][n][8 halfs].
 //   warps 2-5   activation transform: read the [MT*128 + (taps-1)*dil] x 16-channel slab of a K-block ONCE from global
 //               (float4, one K-block of register prefetch), apply the input activation, split hi/lo and store both in the
-//               UMMA no-swizzle K-major layout [16-byte K-chunk][row][4 floats].  There a core matrix (8 rows x 16 B)
+//               UMMA no-swizzle K-major layout [16-byte K-chunk][row][8 halfs].  There a core matrix (8 rows x 16 B)
 //               starting at ANY row is 128 contiguous bytes, so each conv tap is just the same slab with the descriptor start
 //               address advanced by tap*dil rows: the slab is loaded and split once per K-block, not once per tap.
-//   warp 1      MMA issuer (one thread): per weight stage MT * 2 (K=8 steps) * 3 (split terms) tcgen05.mma, M=128, N=NB,
+//   warp 1      MMA issuer (one elected thread): per weight stage MT * 3 (split terms) tcgen05.mma kind::f16, M=128, N=NB, K=16,
 //               accumulating into one of two TMEM accumulator sets; tcgen05.commit releases slab / weight stages and
 //               publishes the accumulators.
 //   warps 6-9   epilogue: tcgen05.ld (thread == output row) -> per-warp 32x36 smem transpose so that 8 lanes cover one
 //               row's 128 bytes -> bias / activation / residual / alpha / accumulate / pad-row mask -> full-line global I/O.
 //               Runs on work item i while the MMAs of item i+1 fill the other accumulator set.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace fs2 {
 
-constexpr int TC_KB = 16;          // input channels per K-block (two K=8 TF32 MMAs)
-constexpr int TC_CHUNKS = TC_KB / 4;
+constexpr int TC_KB = 16;          // input channels per K-block (one K=16 FP16 MMA per split term)
+constexpr int TC_CHUNKS = TC_KB / 8;  // 16-byte K-chunks (8 halfs) per K-block
 constexpr int TC_SA_MAX = 4;       // activation slab stages (runtime p.SA)
 constexpr int TC_SB_MAX = 8;       // weight stages (runtime p.SB)
 constexpr int TC_THREADS = 320;
-constexpr int TC_LD = 10;          // 16-byte global loads per transform thread per K-block (slabs of <= 320 rows)
+constexpr int TC_LD = 5;           // (row, K-chunk) items = 2 float4 loads each per transform thread per K-block (slabs of <= 320 rows)
+constexpr int TC_HDR = 128;        // bytes of header in front of the weight tiles: float[0] = 1 / weight scale
 constexpr int TC_STAGE_FLOATS = 32 * 36;   // per-epilogue-warp transpose tile
 
 struct TcP {
@@ -50,7 +59,7 @@ struct TcP {
   int MT;                          // 128-row tiles per work item
   int TG;                          // accumulators per tile: 1 = all split terms together, 2 = {hi*hi | cross}, 3 = one each
   int SA, SB;                      // ring depths
-  int R;                           // slab rows held in smem (>= MT*128 + (taps-1)*dil, R % 8 == 2)
+  int R;                           // slab rows held in smem (>= MT*128 + (taps-1)*dil, R % 8 == 4)
   int tiles_per_batch;             // work items per utterance
   int n_items;                     // total work items = (N/NB) * B * tiles_per_batch
   int acc_stride;                  // TMEM columns between accumulators
@@ -91,11 +100,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -120,7 +129,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // UMMA shared-memory descriptor, no-swizzle K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
-// LBO = byte distance between the two 16-byte K-chunks of one K=8 (TF32) MMA, SBO = byte distance between 8-row groups.
+// LBO = byte distance between the two 16-byte K-chunks of one K=16 (FP16) MMA, SBO = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
@@ -130,9 +139,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;                 // layout_type = SWIZZLE_NONE (0), base_offset = 0
 }
 
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16 with FP16 operands (a_format = b_format = 0), fp32 accumulate, A and B K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 struct Item { int nblk, b, t0; };
@@ -158,7 +167,7 @@ __device__ __forceinline__ float tc_act(float v, float slope) {
 // W = 32: 8 lanes per row, 4 rows per pass, 8 passes.  W = 16: 4 lanes per row, 8 rows per pass, 4 passes.
 template <int ACT, int W, bool FULL>
 __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, float* stage, int lane, float* yptr, const float* rptr,
-                                                  const float* bias, int rows_live, int rows_valid) {
+                                                  const float* bias, int rows_live, int rows_valid, float inv_ws) {
   constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
   {
     uint32_t v[32];
@@ -202,10 +211,10 @@ __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, 
     if (FULL || r < rows_valid) {
       const float4 a = *reinterpret_cast<const float4*>(stage + r * 36 + (lane % LPR) * 4);
       float4 o;
-      o.x = (tc_act<ACT>(a.x + bv.x, slope) + rv[k].x) * alpha + yv[k].x;
-      o.y = (tc_act<ACT>(a.y + bv.y, slope) + rv[k].y) * alpha + yv[k].y;
-      o.z = (tc_act<ACT>(a.z + bv.z, slope) + rv[k].z) * alpha + yv[k].z;
-      o.w = (tc_act<ACT>(a.w + bv.w, slope) + rv[k].w) * alpha + yv[k].w;
+      o.x = (tc_act<ACT>(fmaf(a.x, inv_ws, bv.x), slope) + rv[k].x) * alpha + yv[k].x;   // inv_ws is a power of two: exact
+      o.y = (tc_act<ACT>(fmaf(a.y, inv_ws, bv.y), slope) + rv[k].y) * alpha + yv[k].y;
+      o.z = (tc_act<ACT>(fmaf(a.z, inv_ws, bv.z), slope) + rv[k].z) * alpha + yv[k].z;
+      o.w = (tc_act<ACT>(fmaf(a.w, inv_ws, bv.w), slope) + rv[k].w) * alpha + yv[k].w;
       if (!FULL && r >= rows_live) o = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(yptr + k * ystep) = o;
     }
@@ -214,7 +223,7 @@ __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, 
 }
 
 template <int ACT>
-__device__ __forceinline__ void tc_epilogue_item(const TcP& p, uint32_t tmem_acc, float* stage, int q, int lane, const Item& it) {
+__device__ __forceinline__ void tc_epilogue_item(const TcP& p, uint32_t tmem_acc, float* stage, int q, int lane, const Item& it, float inv_ws) {
   const int NB = p.NB, n0 = it.nblk * NB;
   const int len_b = p.row_lens ? min(p.row_lens[it.b], p.T) : p.T;
   for (int mt = 0; mt < p.MT; mt++) {
@@ -232,10 +241,10 @@ __device__ __forceinline__ void tc_epilogue_item(const TcP& p, uint32_t tmem_acc
       const float* rptr = p.res ? p.res + (long long)it.b * p.rbs + (long long)(row0 + rr) * p.rrs + n0 + c + cc : nullptr;
       const float* bias = p.bias ? p.bias + n0 + c + cc : nullptr;
       if (w == 32) {
-        if (full) tc_epilogue_block<ACT, 32, true>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid);
-        else tc_epilogue_block<ACT, 32, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid);
+        if (full) tc_epilogue_block<ACT, 32, true>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws);
+        else tc_epilogue_block<ACT, 32, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws);
       } else {
-        tc_epilogue_block<ACT, 16, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid);
+        tc_epilogue_block<ACT, 16, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws);
       }
     }
   }
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       uint32_t itB = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int nblk = item / (p.B * p.tiles_per_batch);
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + TC_HDR + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
         for (int kb = 0; kb < KBLOCKS; kb++) {
           for (int tap = 0; tap < p.taps; tap++, itB++) {
             const uint32_t s = itB % SB;
@@ -304,9 +313,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     // the tensor pipe (a generic address computation per MMA was measured to be the bottleneck).
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-    const uint32_t idesc = umma_idesc_tf32(NB);
+    const uint32_t idesc = umma_idesc_f16(NB);
     const uint64_t a_const = umma_desc(0, (uint32_t)R * 16, 128), b_const = umma_desc(0, (uint32_t)NB * 16, 128);
-    const uint32_t a_kk = 2u * (uint32_t)R, b_kk = 2u * (uint32_t)NB;       // two 16-byte K-chunks per K=8 MMA, in 16-byte units
     const uint32_t tile_cols = (uint32_t)(TG * p.acc_stride);
     const uint32_t g_cross = TG >= 2 ? (uint32_t)p.acc_stride : 0u;            // lo*hi (and hi*lo when TG == 2)
     const uint32_t g_cross2 = TG == 3 ? 2u * (uint32_t)p.acc_stride : g_cross;  // hi*lo
@@ -333,19 +341,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
             const uint32_t first = (kb | tap) ? 1u : 0u;
             // consecutive MMAs alternate between tiles / accumulator groups
 #pragma unroll
-            for (int kk = 0; kk < TC_KB / 8; kk++) {
-              const uint32_t acc_kk = (first | (uint32_t)kk) ? 1u : 0u;
-              const uint64_t bh = b_hi + kk * b_kk, bl = b_lo + kk * b_kk;
+            for (int mt = 0; mt < MT; mt++)            // A_lo * B_hi
+              tc_mma_f16(d0 + mt * tile_cols + g_cross, al0 + mt * 128, b_hi, idesc, first);
 #pragma unroll
-              for (int mt = 0; mt < MT; mt++)          // A_lo * B_hi
-                tc_mma_tf32(d0 + mt * tile_cols + g_cross, al0 + mt * 128 + kk * a_kk, bh, idesc, acc_kk);
+            for (int mt = 0; mt < MT; mt++)            // A_hi * B_hi
+              tc_mma_f16(d0 + mt * tile_cols, ah0 + mt * 128, b_hi, idesc, TG >= 2 ? first : 1u);
 #pragma unroll
-              for (int mt = 0; mt < MT; mt++)          // A_hi * B_hi
-                tc_mma_tf32(d0 + mt * tile_cols, ah0 + mt * 128 + kk * a_kk, bh, idesc, TG >= 2 ? acc_kk : 1u);
-#pragma unroll
-              for (int mt = 0; mt < MT; mt++)          // A_hi * B_lo
-                tc_mma_tf32(d0 + mt * tile_cols + g_cross2, ah0 + mt * 128 + kk * a_kk, bl, idesc, TG == 3 ? acc_kk : 1u);
-            }
+            for (int mt = 0; mt < MT; mt++)            // A_hi * B_lo
+              tc_mma_f16(d0 + mt * tile_cols + g_cross2, ah0 + mt * 128, b_lo, idesc, TG == 3 ? first : 1u);
             tc_commit(&emptyB[sb]);                    // weight stage free once these MMAs retire
           }
           __syncwarp();
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const int items = rows_needed * TC_CHUNKS;
     // One K-block of register prefetch: the loads of the next K-block (possibly of the next work item) are issued right
     // after the current one has been stored, so their latency is spent while waiting for the slab stage to be released.
-    float4 v[TC_LD];
+    float4 v[TC_LD][2];
     auto issue_loads = [&](int item, int kb) {
       const Item it = decode_item(p, item);
       const float* xb = p.x + (long long)it.b * p.xbs + kb * TC_KB;
@@ -371,10 +374,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
 #pragma unroll
       for (int u = 0; u < TC_LD; u++) {
         const int idx = u * 128 + wt;
-        const int row = idx >> 2, ch = idx & 3;
+        const int row = idx >> 1, ch = idx & 1;
         const int t = t_first + row;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < items && t >= 0 && t < p.T) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * p.xrs + ch * 4));
+        v[u][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u][1] = v[u][0];
+        if (idx < items && t >= 0 && t < p.T) {
+          const float4* src = reinterpret_cast<const float4*>(xb + (long long)t * p.xrs + ch * 8);
+          v[u][0] = __ldg(src);
+          v[u][1] = __ldg(src + 1);
+        }
       }
     };
     int item = blockIdx.x, kb = 0;
@@ -391,20 +399,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       for (int u = 0; u < TC_LD; u++) {
         const int idx = u * 128 + wt;
         if (idx >= items) continue;
-        const int row = idx >> 2, ch = idx & 3;
-        float4 a = v[u];
-        if (lrelu_in) {
-          a.x = a.x > 0.f ? a.x : a.x * in_slope; a.y = a.y > 0.f ? a.y : a.y * in_slope;
-          a.z = a.z > 0.f ? a.z : a.z * in_slope; a.w = a.w > 0.f ? a.w : a.w * in_slope;
+        const int row = idx >> 1, ch = idx & 1;
+        float f[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float a0 = f[2 * j], a1 = f[2 * j + 1];
+          if (lrelu_in) {
+            a0 = a0 > 0.f ? a0 : a0 * in_slope;
+            a1 = a1 > 0.f ? a1 : a1 * in_slope;
+          }
+          a0 = fminf(fmaxf(a0, -65504.f), 65504.f);   // fp16 range
+          a1 = fminf(fmaxf(a1, -65504.f), 65504.f);
+          const __half2 h2 = __floats2half2_rn(a0, a1);
+          const float2 hf = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);   // a - hi is exact in fp32
+          hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
         }
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u); l.x = a.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u); l.y = a.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u); l.z = a.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u); l.w = a.w - h.w;
         const uint32_t off = ((uint32_t)ch * R + row) * 16;
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
+        *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
       fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&fullA[sa]);
@@ -416,6 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     float* stage = stage_all + (warp - 6) * TC_STAGE_FLOATS;
+    const float inv_ws = __ldg(p.wt);                  // header: 1 / (power-of-two weight scale)
     uint32_t itT = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++) {
       const uint32_t buf = itT & 1;
@@ -424,10 +440,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       tc_fence_after();
       const uint32_t acc = tmem + buf * acc_set;
       switch (p.out_act) {                             // uniform branch: keeps tanhf out of the other variants' inner loops
-        case FS2_ACT_RELU: tc_epilogue_item<FS2_ACT_RELU>(p, acc, stage, q, lane, it); break;
-        case FS2_ACT_TANH: tc_epilogue_item<FS2_ACT_TANH>(p, acc, stage, q, lane, it); break;
-        case FS2_ACT_LRELU: tc_epilogue_item<FS2_ACT_LRELU>(p, acc, stage, q, lane, it); break;
-        default: tc_epilogue_item<FS2_ACT_NONE>(p, acc, stage, q, lane, it); break;
+        case FS2_ACT_RELU: tc_epilogue_item<FS2_ACT_RELU>(p, acc, stage, q, lane, it, inv_ws); break;
+        case FS2_ACT_TANH: tc_epilogue_item<FS2_ACT_TANH>(p, acc, stage, q, lane, it, inv_ws); break;
+        case FS2_ACT_LRELU: tc_epilogue_item<FS2_ACT_LRELU>(p, acc, stage, q, lane, it, inv_ws); break;
+        default: tc_epilogue_item<FS2_ACT_NONE>(p, acc, stage, q, lane, it, inv_ws); break;
       }
       tc_fence_before();
       mbar_arrive(&accEmpty[buf]);                     // all of this thread's tcgen05.ld of the set have completed
@@ -464,7 +480,7 @@ bool conv_tc_supported(const fs2_conv1d_args* a) {
   if ((a->x_row_stride & 3) || (a->x_batch_stride & 3) || (a->y_row_stride & 3) || (a->y_batch_stride & 3)) return false;
   if (a->res && ((a->res_row_stride & 3) || (a->res_batch_stride & 3))) return false;
   if (a->in_act != FS2_ACT_NONE && a->in_act != FS2_ACT_LRELU) return false;
-  if ((a->taps - 1) * a->dilation > TC_LD * 32 - 128) return false;
+  if ((a->taps - 1) * a->dilation > TC_LD * 64 - 128) return false;
   return true;
 }
 
@@ -504,9 +520,9 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   const int tiles128 = (a->T + 127) / 128;
   int mt = 2;                                          // two accumulator sets of MT tiles: 2*MT*acc_stride <= 512 columns
   if (mt > tiles128) mt = tiles128;
-  if (mt * 128 + halo > TC_LD * 32) mt = 1;            // the transform holds one slab K-block in registers
+  if (mt * 128 + halo > TC_LD * 64) mt = 1;            // the transform holds one slab K-block in registers
   int R = mt * 128 + halo;
-  R += (10 - (R & 7)) & 7;                             // R % 8 == 2: conflict-free transform stores
+  R += (12 - (R & 7)) & 7;                             // R % 8 == 4: conflict-free transform stores (2 chunks per row)
   p.MT = mt; p.R = R;
   p.TG = p.acc_stride <= 32 ? 3 : (p.acc_stride <= 64 ? 2 : 1);   // spread split terms while two sets still fit in 512 columns
   const size_t fixed = 4 * TC_STAGE_FLOATS * sizeof(float) + (2 * TC_SA_MAX + 2 * TC_SB_MAX + 4) * 8 + 16;

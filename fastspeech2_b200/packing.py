@@ -6,6 +6,7 @@ PostNet convs, weight-norm folded, ConvTranspose1d split into its two 2-tap phas
 """
 from __future__ import annotations
 
+import math
 from typing import Callable, Dict
 
 import torch
@@ -35,23 +36,36 @@ def conv_tc_block(n_out: int) -> int:
     return 0
 
 
-def split_tf32(w: Tensor):
-    """x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi exact in fp32."""
-    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
-    return hi, w - hi
+TC_HEADER_BYTES = 128
+
+
+def split_fp16(w: Tensor):
+    """Per-layer power-of-two scale s and the split s*w = hi + lo, hi = fp16(s*w), lo = fp16(s*w - hi)  (s*w - hi is exact
+    in fp32).  s puts max|s*w| in [8192, 16384] so that lo stays in fp16's normal range; 1/s is applied in the epilogue."""
+    m = float(w.abs().max())
+    s = 1.0 if m == 0.0 or not math.isfinite(m) else 2.0 ** math.floor(math.log2(16384.0 / m))
+    ws = w.float() * s
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    return hi, lo, s
 
 
 def pack_conv_tc(w: Tensor):
-    """[taps][Cin][N] -> tcgen05 tile layout [N/NB][taps][Cin/16][hi|lo][4 K-chunks][NB][4 floats] (see include/fs2b200.h).
+    """[taps][Cin][N] fp32 -> byte buffer for the tcgen05 kernel (see include/fs2b200.h):
+         128-byte header (float32[0] = 1/scale)  |  [N/NB][taps][Cin/16][hi|lo][2 K-chunks][NB][8 halfs]
+    Every (tap, 16-channel K-block) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major, fp16).
     Returns None when the shape is not served by the tensor-core kernel."""
     taps, cin, n = w.shape
     nb = conv_tc_block(n)
     if nb == 0 or cin % 16:
         return None
-    hi, lo = split_tf32(w)
+    hi, lo, s = split_fp16(w)
     both = torch.stack([hi, lo], dim=0)                                  # [2][taps][Cin][N]
-    t = both.reshape(2, taps, cin // 16, 4, 4, n // nb, nb)              # [2][tap][kb][chunk][e][nblk][nn]
-    return t.permute(5, 1, 2, 0, 3, 6, 4).contiguous()                   # [nblk][tap][kb][2][chunk][nn][e]
+    t = both.reshape(2, taps, cin // 16, 2, 8, n // nb, nb)              # [2][tap][kb][chunk][e][nblk][nn]
+    tiles = t.permute(5, 1, 2, 0, 3, 6, 4).contiguous()                  # [nblk][tap][kb][2][chunk][nn][e]
+    header = torch.zeros(TC_HEADER_BYTES // 4, dtype=torch.float32, device=w.device)
+    header[0] = 1.0 / s
+    return torch.cat([header.view(torch.uint8), tiles.view(torch.uint8).reshape(-1)])
 
 
 def add_tc_tiles(pk: Dict[str, Tensor], keys) -> None:

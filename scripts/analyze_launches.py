@@ -15,4 +15,4 @@ if len(sys.argv) > 2:
     i = 0
     for n, g, t in rows:
         if 'conv_' in n and 'post' not in n:
-            print(i, n.split('(')[0][-18:], g, f"{t/1e3:9.1f} us"); i += 1
+            print(i, n.split("(")[0][-14:], g, f"{t/1e3:9.1f} us"); i += 1
