@@ -16,15 +16,15 @@
 // one utterance x one block of NB <= 128 output channels); four roles overlap through mbarrier rings:
 //   warp 0      weight producer: every (tap, 16-channel K-block) weight stage is ONE cp.async.bulk (TMA bulk engine) of a
 //               host-pre-split, host-pre-tiled smem image  [hi|lo][16-byte K-chunk][n][8 halfs].
-//   warps 2-5   activation transform: read the [MT*128 + (taps-1)*dil] x 16-channel slab of a K-block ONCE from global
-//               (float4, one K-block of register prefetch), apply the input activation, split hi/lo and store both in the
+//   warps 2-9   activation transform: read the [MT*128 + (taps-1)*dil] x 16-channel slab of a K-block ONCE from global
+//               (float4, a 3-deep register ring of K-blocks in flight: ~60 KB of loads per SM, what HBM latency x bandwidth needs), apply the input activation, split hi/lo and store both in the
 //               UMMA no-swizzle K-major layout [16-byte K-chunk][row][8 halfs].  There a core matrix (8 rows x 16 B)
 //               starting at ANY row is 128 contiguous bytes, so each conv tap is just the same slab with the descriptor start
 //               address advanced by tap*dil rows: the slab is loaded and split once per K-block, not once per tap.
 //   warp 1      MMA issuer (one elected thread): per weight stage MT * 3 (split terms) tcgen05.mma kind::f16, M=128, N=NB, K=16,
 //               accumulating into one of two TMEM accumulator sets; tcgen05.commit releases slab / weight stages and
 //               publishes the accumulators.
-//   warps 6-9   epilogue: tcgen05.ld (thread == output row) -> per-warp 32x36 smem transpose so that 8 lanes cover one
+//   warps 10-13 epilogue: tcgen05.ld (thread == output row) -> per-warp 32x36 smem transpose so that 8 lanes cover one
 //               row's 128 bytes -> bias / activation / residual / alpha / accumulate / pad-row mask -> full-line global I/O.
 //               Runs on work item i while the MMAs of item i+1 fill the other accumulator set.
 #include <cuda_fp16.h>
@@ -37,8 +37,11 @@ constexpr int TC_KB = 16;          // input channels per K-block (one K=16 FP16 
 constexpr int TC_CHUNKS = TC_KB / 8;  // 16-byte K-chunks (8 halfs) per K-block
 constexpr int TC_SA_MAX = 4;       // activation slab stages (runtime p.SA)
 constexpr int TC_SB_MAX = 8;       // weight stages (runtime p.SB)
-constexpr int TC_THREADS = 320;
-constexpr int TC_LD = 5;           // (row, K-chunk) items = 2 float4 loads each per transform thread per K-block (slabs of <= 320 rows)
+constexpr int TC_TW = 8;            // transform warps
+constexpr int TC_TTHREADS = TC_TW * 32;
+constexpr int TC_THREADS = 64 + TC_TTHREADS + 128;   // producer + MMA warps, transform warps, 4 epilogue warps
+constexpr int TC_DEPTH = 3;         // K-blocks of activation loads in flight per transform thread (register ring)
+constexpr int TC_LD = 3;           // (row, K-chunk) items (2 float4 loads each) per transform thread per K-block: 256 * 3 / 2 >= 384 rows
 constexpr int TC_HDR = 128;        // bytes of header in front of the weight tiles: float[0] = 1 / weight scale
 constexpr int TC_STAGE_FLOATS = 32 * 36;   // per-epilogue-warp transpose tile
 
@@ -64,6 +67,8 @@ struct TcP {
   int n_items;                     // total work items = (N/NB) * B * tiles_per_batch
   int acc_stride;                  // TMEM columns between accumulators
   int tmem_cols;                   // power of two >= 2*MT*TG*acc_stride
+  long long* trace;                // debug: [CTA][16 items][8] globaltimer stamps, or NULL
+  unsigned variant;                // debug knobs: 1 = transform skips global loads, 2 = transform skips the split math, 4 = epilogue skips global stores
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -144,6 +149,25 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// debug timeline: slot 0/1 transform first-load-issue / last-store of the item, 2/3 MMA start / all issued, 4/5 epilogue start / end
+#define TC_STAMP(il, slot)                                                                       \
+  do {                                                                                           \
+    if (p.trace && (il) < 16) p.trace[((long long)blockIdx.x * 16 + (il)) * 8 + (slot)] = gtime(); \
+  } while (0)
+
+// mbarrier ring cursor without runtime div/mod (an integer division per tap was on the MMA issuer's critical path)
+struct Ring {
+  uint32_t idx = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n) {
+    if (++idx == n) { idx = 0; phase ^= 1u; }
+  }
+};
+
 struct Item { int nblk, b, t0; };
 __device__ __forceinline__ Item decode_item(const TcP& p, int item) {
   const int per_blk = p.B * p.tiles_per_batch;
@@ -189,34 +213,39 @@ __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, 
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias));
   const long long ystep = (long long)RPI * p.yrs, rstep = (long long)RPI * p.rrs;
-  float4 rv[ITERS], yv[ITERS];
+  constexpr int HALF = ITERS / 2;
 #pragma unroll
-  for (int k = 0; k < ITERS; k++) {
-    rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    yv[k] = rv[k];
-  }
-  if (rptr) {
+  for (int h = 0; h < 2; h++) {                        // two half-blocks: bounds the registers held by in-flight loads
+    float4 rv[HALF], yv[HALF];
 #pragma unroll
-    for (int k = 0; k < ITERS; k++)
-      if (FULL || k * RPI + rr < rows_valid) rv[k] = *reinterpret_cast<const float4*>(rptr + k * rstep);
-  }
-  if (p.accumulate) {
+    for (int k = 0; k < HALF; k++) {
+      rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      yv[k] = rv[k];
+    }
+    if (rptr) {
 #pragma unroll
-    for (int k = 0; k < ITERS; k++)
-      if (FULL || k * RPI + rr < rows_valid) yv[k] = *reinterpret_cast<const float4*>(yptr + k * ystep);
-  }
+      for (int k = 0; k < HALF; k++)
+        if (FULL || (h * HALF + k) * RPI + rr < rows_valid) rv[k] = *reinterpret_cast<const float4*>(rptr + (h * HALF + k) * rstep);
+    }
+    if (p.accumulate) {
 #pragma unroll
-  for (int k = 0; k < ITERS; k++) {
-    const int r = k * RPI + rr;
-    if (FULL || r < rows_valid) {
-      const float4 a = *reinterpret_cast<const float4*>(stage + r * 36 + (lane % LPR) * 4);
-      float4 o;
-      o.x = (tc_act<ACT>(fmaf(a.x, inv_ws, bv.x), slope) + rv[k].x) * alpha + yv[k].x;   // inv_ws is a power of two: exact
-      o.y = (tc_act<ACT>(fmaf(a.y, inv_ws, bv.y), slope) + rv[k].y) * alpha + yv[k].y;
-      o.z = (tc_act<ACT>(fmaf(a.z, inv_ws, bv.z), slope) + rv[k].z) * alpha + yv[k].z;
-      o.w = (tc_act<ACT>(fmaf(a.w, inv_ws, bv.w), slope) + rv[k].w) * alpha + yv[k].w;
-      if (!FULL && r >= rows_live) o = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(yptr + k * ystep) = o;
+      for (int k = 0; k < HALF; k++)
+        if (FULL || (h * HALF + k) * RPI + rr < rows_valid) yv[k] = *reinterpret_cast<const float4*>(yptr + (h * HALF + k) * ystep);
+    }
+#pragma unroll
+    for (int k = 0; k < HALF; k++) {
+      const int kk = h * HALF + k;
+      const int r = kk * RPI + rr;
+      if (FULL || r < rows_valid) {
+        const float4 a = *reinterpret_cast<const float4*>(stage + r * 36 + (lane % LPR) * 4);
+        float4 o;
+        o.x = (tc_act<ACT>(fmaf(a.x, inv_ws, bv.x), slope) + rv[k].x) * alpha + yv[k].x;   // inv_ws is a power of two: exact
+        o.y = (tc_act<ACT>(fmaf(a.y, inv_ws, bv.y), slope) + rv[k].y) * alpha + yv[k].y;
+        o.z = (tc_act<ACT>(fmaf(a.z, inv_ws, bv.z), slope) + rv[k].z) * alpha + yv[k].z;
+        o.w = (tc_act<ACT>(fmaf(a.w, inv_ws, bv.w), slope) + rv[k].w) * alpha + yv[k].w;
+        if (!FULL && r >= rows_live) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(p.variant & 4u)) *reinterpret_cast<float4*>(yptr + kk * ystep) = o;
+      }
     }
   }
   __syncwarp();   // the staging tile is rewritten by the next block
@@ -235,8 +264,8 @@ __device__ __forceinline__ void tc_epilogue_item(const TcP& p, uint32_t tmem_acc
     const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.TG * p.acc_stride);
     for (int c = 0; c < NB; c += 32) {
       const int w = (NB - c) >= 32 ? 32 : 16;          // NB % 16 == 0
-      const int lpr = w >> 2;
-      const int rr = lane / lpr, cc = (lane % lpr) * 4;
+      const int sh = w == 32 ? 3 : 2;                  // lanes per row = 8 or 4
+      const int rr = lane >> sh, cc = (lane & ((1 << sh) - 1)) * 4;
       float* yptr = p.y + (long long)it.b * p.ybs + (long long)(row0 + rr) * p.yrs + n0 + c + cc;
       const float* rptr = p.res ? p.res + (long long)it.b * p.rbs + (long long)(row0 + rr) * p.rrs + n0 + c + cc : nullptr;
       const float* bias = p.bias ? p.bias + n0 + c + cc : nullptr;
@@ -272,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   const int KBLOCKS = p.Cin / TC_KB;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < TC_SA_MAX; i++) { mbar_init(&fullA[i], 128); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < TC_SA_MAX; i++) { mbar_init(&fullA[i], TC_TTHREADS); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < TC_SB_MAX; i++) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
     for (int i = 0; i < 2; i++) { mbar_init(&accFull[i], 1); mbar_init(&accEmpty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -291,18 +320,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     // ===================== weight-stage producer (TMA bulk copies) =====================
     if (lane == 0) {
       const uint32_t stage_bytes = 2 * b_plane;
-      uint32_t itB = 0;
+      Ring rb;
+      const int per_blk = p.B * p.tiles_per_batch;
+      int nblk = (int)blockIdx.x / per_blk, rem = (int)blockIdx.x - nblk * per_blk;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int nblk = item / (p.B * p.tiles_per_batch);
         const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + TC_HDR + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
         for (int kb = 0; kb < KBLOCKS; kb++) {
-          for (int tap = 0; tap < p.taps; tap++, itB++) {
-            const uint32_t s = itB % SB;
-            mbar_wait(&emptyB[s], ((itB / SB) & 1) ^ 1);
-            mbar_expect_tx(&fullB[s], stage_bytes);
-            bulk_g2s(b_base + (size_t)s * stage_bytes, wsrc + ((size_t)tap * KBLOCKS + kb) * stage_bytes, stage_bytes, &fullB[s]);
+          const unsigned char* src = wsrc + (size_t)kb * stage_bytes;
+          for (int tap = 0; tap < p.taps; tap++, src += (size_t)KBLOCKS * stage_bytes) {
+            mbar_wait(&emptyB[rb.idx], rb.phase ^ 1);
+            mbar_expect_tx(&fullB[rb.idx], stage_bytes);
+            bulk_g2s(b_base + (size_t)rb.idx * stage_bytes, src, stage_bytes, &fullB[rb.idx]);
+            rb.advance(SB);
           }
         }
+        rem += (int)gridDim.x;
+        while (rem >= per_blk) { rem -= per_blk; nblk++; }
       }
     }
   } else if (warp == 1) {
@@ -318,26 +351,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const uint32_t tile_cols = (uint32_t)(TG * p.acc_stride);
     const uint32_t g_cross = TG >= 2 ? (uint32_t)p.acc_stride : 0u;            // lo*hi (and hi*lo when TG == 2)
     const uint32_t g_cross2 = TG == 3 ? 2u * (uint32_t)p.acc_stride : g_cross;  // hi*lo
-    uint32_t itA = 0, itB = 0, itT = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++) {
-      const uint32_t buf = itT & 1;
-      mbar_wait(&accEmpty[buf], ((itT >> 1) & 1) ^ 1);            // epilogue has drained this accumulator set
+    Ring ra, rb, rt;
+    uint32_t itT = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
+      const uint32_t buf = rt.idx;
+      mbar_wait(&accEmpty[buf], rt.phase ^ 1);                    // epilogue has drained this accumulator set
       tc_fence_after();
       const uint32_t d0 = tmem + buf * acc_set;
-      for (int kb = 0; kb < KBLOCKS; kb++, itA++) {
-        const uint32_t sa = itA % SA;
-        mbar_wait(&fullA[sa], (itA / SA) & 1);
+      if (leader) TC_STAMP((int)itT, 2);
+      for (int kb = 0; kb < KBLOCKS; kb++, ra.advance(SA)) {
+        const uint32_t sa = ra.idx;
+        mbar_wait(&fullA[sa], ra.phase);
         tc_fence_after();
         const uint64_t a_hi = a_const | (uint64_t)(smem_u32(a_base + (size_t)sa * 2 * a_plane) >> 4);
         const uint64_t a_lo = a_hi + (a_plane >> 4);
-        for (int tap = 0; tap < p.taps; tap++, itB++) {
-          const uint32_t sb = itB % SB;
-          mbar_wait(&fullB[sb], (itB / SB) & 1);
+        uint32_t row_off = 0;
+        for (int tap = 0; tap < p.taps; tap++, rb.advance(SB), row_off += (uint32_t)p.dil) {
+          const uint32_t sb = rb.idx;
+          mbar_wait(&fullB[sb], rb.phase);
           tc_fence_after();
           if (leader) {
             const uint64_t b_hi = b_const | (uint64_t)(smem_u32(b_base + (size_t)sb * 2 * b_plane) >> 4);
             const uint64_t b_lo = b_hi + (b_plane >> 4);
-            const uint64_t ah0 = a_hi + (uint32_t)(tap * p.dil), al0 = a_lo + (uint32_t)(tap * p.dil);
+            const uint64_t ah0 = a_hi + row_off, al0 = a_lo + row_off;
             const uint32_t first = (kb | tap) ? 1u : 0u;
             // consecutive MMAs alternate between tiles / accumulator groups
 #pragma unroll
@@ -357,57 +393,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
         __syncwarp();
       }
       if (leader) tc_commit(&accFull[buf]);            // accumulators of this work item complete
+      if (leader) TC_STAMP((int)itT, 3);
       __syncwarp();
     }
-  } else if (warp < 6) {
-    // ===================== transform warps (activation + hi/lo split) =====================
-    const int wt = tid - 64;                           // 0..127
+  } else if (warp < 2 + TC_TW) {
+    // ===================== transform warps (activation + fp16 hi/lo split) =====================
+    const int wt = tid - 64;                           // 0..TC_TTHREADS-1
     const int rows_needed = MT * 128 + (p.taps - 1) * p.dil;
     const int items = rows_needed * TC_CHUNKS;
-    // One K-block of register prefetch: the loads of the next K-block (possibly of the next work item) are issued right
-    // after the current one has been stored, so their latency is spent while waiting for the slab stage to be released.
-    float4 v[TC_LD][2];
-    auto issue_loads = [&](int item, int kb) {
-      const Item it = decode_item(p, item);
-      const float* xb = p.x + (long long)it.b * p.xbs + kb * TC_KB;
-      const int t_first = it.t0 - p.pad;
-#pragma unroll
-      for (int u = 0; u < TC_LD; u++) {
-        const int idx = u * 128 + wt;
-        const int row = idx >> 1, ch = idx & 1;
-        const int t = t_first + row;
-        v[u][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[u][1] = v[u][0];
-        if (idx < items && t >= 0 && t < p.T) {
-          const float4* src = reinterpret_cast<const float4*>(xb + (long long)t * p.xrs + ch * 8);
-          v[u][0] = __ldg(src);
-          v[u][1] = __ldg(src + 1);
-        }
-      }
-    };
-    int item = blockIdx.x, kb = 0;
-    if (item < p.n_items) issue_loads(item, 0);
-    uint32_t itA = 0;
+    // Register ring of TC_DEPTH K-blocks: the loads of K-block seq + TC_DEPTH (possibly of a later work item) are issued as
+    // soon as K-block seq has been converted and stored, so ~TC_DEPTH slabs of loads stay in flight per SM.
+    float4 v[TC_DEPTH][TC_LD][2];
     const bool lrelu_in = p.in_act == FS2_ACT_LRELU;
     const float in_slope = p.in_slope;
-    while (item < p.n_items) {
-      const uint32_t sa = itA % SA;
-      mbar_wait(&emptyA[sa], ((itA / SA) & 1) ^ 1);
+    // per-thread (row, chunk) slots: fixed for the whole kernel
+    int rowu[TC_LD], offu[TC_LD];
+#pragma unroll
+    for (int u = 0; u < TC_LD; u++) {
+      const int idx = u * TC_TTHREADS + wt;
+      rowu[u] = idx < items ? (idx >> 1) : -1;
+      offu[u] = (((idx & 1) * R) + (idx >> 1)) * 16;
+    }
+    // load cursor (runs TC_DEPTH K-blocks ahead of the store cursor); no divisions on the per-K-block path
+    int l_item = blockIdx.x, l_kb = 0;
+    const float* l_xb = nullptr;
+    int l_tfirst = 0;
+    auto l_set_item = [&]() {
+      if (l_item < p.n_items) {
+        const Item it = decode_item(p, l_item);
+        l_xb = p.x + (long long)it.b * p.xbs + (wt & 1) * 8;
+        l_tfirst = it.t0 - p.pad;
+      }
+    };
+    l_set_item();
+    auto issue_loads = [&](float4 (&dst)[TC_LD][2]) {   // loads K-block (l_item, l_kb), then advances the load cursor
+      const float* xk = l_xb + l_kb * TC_KB;
+#pragma unroll
+      for (int u = 0; u < TC_LD; u++) {
+        const int t = l_tfirst + rowu[u];
+        dst[u][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[u][1] = dst[u][0];
+        if (rowu[u] >= 0 && t >= 0 && t < p.T && !(p.variant & 1u)) {
+          const float4* src = reinterpret_cast<const float4*>(xk + (long long)t * p.xrs);
+          dst[u][0] = __ldg(src);
+          dst[u][1] = __ldg(src + 1);
+        }
+      }
+      if (++l_kb == KBLOCKS) { l_kb = 0; l_item += gridDim.x; l_set_item(); }
+    };
+    auto convert_store = [&](const float4 (&src)[TC_LD][2], uint32_t sa) {
       unsigned char* hi = a_base + (size_t)sa * 2 * a_plane;
       unsigned char* lo = hi + a_plane;
 #pragma unroll
       for (int u = 0; u < TC_LD; u++) {
-        const int idx = u * 128 + wt;
-        if (idx >= items) continue;
-        const int row = idx >> 1, ch = idx & 1;
-        float f[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+        if (rowu[u] < 0) continue;
+        const float f[8] = {src[u][0].x, src[u][0].y, src[u][0].z, src[u][0].w, src[u][1].x, src[u][1].y, src[u][1].z, src[u][1].w};
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           float a0 = f[2 * j], a1 = f[2 * j + 1];
           if (lrelu_in) {
-            a0 = a0 > 0.f ? a0 : a0 * in_slope;
-            a1 = a1 > 0.f ? a1 : a1 * in_slope;
+            a0 = fmaxf(a0, a0 * in_slope);               // leaky_relu for 0 <= slope <= 1
+            a1 = fmaxf(a1, a1 * in_slope);
           }
           a0 = fminf(fmaxf(a0, -65504.f), 65504.f);   // fp16 range
           a1 = fminf(fmaxf(a1, -65504.f), 65504.f);
@@ -417,28 +464,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
           hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
           lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
         }
-        const uint32_t off = ((uint32_t)ch * R + row) * 16;
-        *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        if (p.variant & 2u) {                          // debug: no split math
+          *reinterpret_cast<float4*>(hi + offu[u]) = src[u][0];
+          *reinterpret_cast<float4*>(lo + offu[u]) = src[u][1];
+          continue;
+        }
+        *reinterpret_cast<uint4*>(hi + offu[u]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(lo + offu[u]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
-      fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(&fullA[sa]);
-      itA++;
-      if (++kb == KBLOCKS) { kb = 0; item += gridDim.x; }
-      if (item < p.n_items) issue_loads(item, kb);
+    };
+    const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_items * KBLOCKS;
+#pragma unroll
+    for (int d = 0; d < TC_DEPTH; d++)
+      if (d < total) issue_loads(v[d]);
+    Ring ra;
+    int s_kb = 0, s_il = 0;                            // store cursor (for the debug timeline only)
+    for (int base = 0; base < total; base += TC_DEPTH) {
+#pragma unroll
+      for (int d = 0; d < TC_DEPTH; d++) {
+        const int seq = base + d;
+        if (seq < total) {
+          if (wt == 0 && s_kb == 0) TC_STAMP(s_il, 0);
+          mbar_wait(&emptyA[ra.idx], ra.phase ^ 1);
+          convert_store(v[d], ra.idx);
+          fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(&fullA[ra.idx]);
+          ra.advance(SA);
+          if (wt == 0 && s_kb == KBLOCKS - 1) TC_STAMP(s_il, 1);
+          if (++s_kb == KBLOCKS) { s_kb = 0; s_il++; }
+          if (seq + TC_DEPTH < total) issue_loads(v[d]);
+        }
+      }
     }
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    float* stage = stage_all + (warp - 6) * TC_STAGE_FLOATS;
+    float* stage = stage_all + (warp - 2 - TC_TW) * TC_STAGE_FLOATS;
     const float inv_ws = __ldg(p.wt);                  // header: 1 / (power-of-two weight scale)
     uint32_t itT = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++) {
-      const uint32_t buf = itT & 1;
+    Ring rt;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
+      const uint32_t buf = rt.idx;
       const Item it = decode_item(p, item);
-      mbar_wait(&accFull[buf], (itT >> 1) & 1);
+      mbar_wait(&accFull[buf], rt.phase);
       tc_fence_after();
       const uint32_t acc = tmem + buf * acc_set;
+      if (warp == 2 + TC_TW && lane == 0) TC_STAMP((int)itT, 4);
       switch (p.out_act) {                             // uniform branch: keeps tanhf out of the other variants' inner loops
         case FS2_ACT_RELU: tc_epilogue_item<FS2_ACT_RELU>(p, acc, stage, q, lane, it, inv_ws); break;
         case FS2_ACT_TANH: tc_epilogue_item<FS2_ACT_TANH>(p, acc, stage, q, lane, it, inv_ws); break;
@@ -447,6 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       }
       tc_fence_before();
       mbar_arrive(&accEmpty[buf]);                     // all of this thread's tcgen05.ld of the set have completed
+      if (warp == 2 + TC_TW && lane == 0) TC_STAMP((int)itT, 5);
     }
   }
 
@@ -459,7 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
 }
 
 // ------------------------------------------------------------------ host side
-long long* g_tc_trace = nullptr;  // debug hook kept for ABI stability (unused by the persistent kernel)
+long long* g_tc_trace = nullptr;  // debug: set through fs2_debug_set_tc_trace (per-item role timeline)
 
 static int pow2_cols(int c) {
   int v = 32;
@@ -480,7 +553,8 @@ bool conv_tc_supported(const fs2_conv1d_args* a) {
   if ((a->x_row_stride & 3) || (a->x_batch_stride & 3) || (a->y_row_stride & 3) || (a->y_batch_stride & 3)) return false;
   if (a->res && ((a->res_row_stride & 3) || (a->res_batch_stride & 3))) return false;
   if (a->in_act != FS2_ACT_NONE && a->in_act != FS2_ACT_LRELU) return false;
-  if ((a->taps - 1) * a->dilation > TC_LD * 64 - 128) return false;
+  if (a->in_act == FS2_ACT_LRELU && !(a->in_slope >= 0.f && a->in_slope <= 1.f)) return false;   // max(x, slope*x) form
+  if ((a->taps - 1) * a->dilation > TC_LD * TC_TTHREADS / TC_CHUNKS - 128) return false;
   return true;
 }
 
@@ -488,7 +562,6 @@ static int g_num_sms = 0;
 
 // `wt` must be the tiled layout produced by fastspeech2_b200.packing.pack_conv_tc (see fs2b200.h)
 int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s) {
-  (void)variant;
   if (!a || !a->x || !wt || !a->y) return FS2_ERR_ARG;
   if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
   if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
@@ -515,12 +588,14 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.res = a->res; p.rbs = a->res_batch_stride; p.rrs = a->res_row_stride;
   p.alpha = a->alpha; p.accumulate = a->accumulate; p.row_lens = a->row_lens;
   p.y = a->y; p.ybs = a->y_batch_stride; p.yrs = a->y_row_stride;
+  p.trace = g_tc_trace;
+  p.variant = variant;
   p.acc_stride = (p.NB + 31) & ~31;
   const int halo = (a->taps - 1) * a->dilation;
   const int tiles128 = (a->T + 127) / 128;
   int mt = 2;                                          // two accumulator sets of MT tiles: 2*MT*acc_stride <= 512 columns
   if (mt > tiles128) mt = tiles128;
-  if (mt * 128 + halo > TC_LD * 64) mt = 1;            // the transform holds one slab K-block in registers
+  if (mt * 128 + halo > TC_LD * TC_TTHREADS / TC_CHUNKS) mt = 1;   // rows one register-ring slot can hold
   int R = mt * 128 + halo;
   R += (12 - (R & 7)) & 7;                             // R % 8 == 4: conflict-free transform stores (2 chunks per row)
   p.MT = mt; p.R = R;
