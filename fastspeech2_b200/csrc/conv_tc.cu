@@ -62,6 +62,7 @@ struct TcP {
   int MT;                          // 128-row tiles per work item
   int TG;                          // accumulators per tile: 1 = all split terms together, 2 = {hi*hi | cross}, 3 = one each
   int SA, SB;                      // ring depths
+  int TPS;                         // conv taps per weight stage (small NB: several taps share one bulk copy / one handshake)
   int R;                           // slab rows held in smem (>= MT*128 + (taps-1)*dil, R % 8 == 4)
   int tiles_per_batch;             // work items per utterance
   int n_items;                     // total work items = (N/NB) * B * tiles_per_batch
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   float* stage_all = reinterpret_cast<float*>(smem_raw);           // [4 warps][32 x 36] epilogue transpose tiles
   unsigned char* a_base = smem_raw + 4 * TC_STAGE_FLOATS * sizeof(float);   // [SA][hi|lo][chunk][R][16 B]
   unsigned char* b_base = a_base + (size_t)SA * 2 * a_plane;       // [SB][hi|lo][chunk][NB][16 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)SB * 2 * b_plane);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)SB * p.TPS * 2 * b_plane);
   uint64_t* fullA = bars;                  // [SA_MAX]
   uint64_t* emptyA = fullA + TC_SA_MAX;    // [SA_MAX]
   uint64_t* fullB = emptyA + TC_SA_MAX;    // [SB_MAX]
@@ -301,9 +302,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   const int KBLOCKS = p.Cin / TC_KB;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < TC_SA_MAX; i++) { mbar_init(&fullA[i], TC_TTHREADS); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < TC_SA_MAX; i++) { mbar_init(&fullA[i], TC_TW); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < TC_SB_MAX; i++) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&accFull[i], 1); mbar_init(&accEmpty[i], 128); }
+    for (int i = 0; i < 2; i++) { mbar_init(&accFull[i], 1); mbar_init(&accEmpty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -319,18 +320,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   if (warp == 0) {
     // ===================== weight-stage producer (TMA bulk copies) =====================
     if (lane == 0) {
-      const uint32_t stage_bytes = 2 * b_plane;
+      const uint32_t stage_bytes = 2 * b_plane;   // one tap of one K-block (hi + lo)
       Ring rb;
       const int per_blk = p.B * p.tiles_per_batch;
       int nblk = (int)blockIdx.x / per_blk, rem = (int)blockIdx.x - nblk * per_blk;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + TC_HDR + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
+        const unsigned char* src = wsrc;           // tiles are ordered [kb][tap]: the taps of one K-block are contiguous
         for (int kb = 0; kb < KBLOCKS; kb++) {
-          const unsigned char* src = wsrc + (size_t)kb * stage_bytes;
-          for (int tap = 0; tap < p.taps; tap++, src += (size_t)KBLOCKS * stage_bytes) {
+          for (int tap = 0; tap < p.taps; tap += p.TPS) {
+            const int n = min(p.TPS, p.taps - tap);
+            const uint32_t bytes = (uint32_t)n * stage_bytes;
             mbar_wait(&emptyB[rb.idx], rb.phase ^ 1);
-            mbar_expect_tx(&fullB[rb.idx], stage_bytes);
-            bulk_g2s(b_base + (size_t)rb.idx * stage_bytes, src, stage_bytes, &fullB[rb.idx]);
+            mbar_expect_tx(&fullB[rb.idx], bytes);
+            bulk_g2s(b_base + (size_t)rb.idx * p.TPS * stage_bytes, src, bytes, &fullB[rb.idx]);
+            src += bytes;
             rb.advance(SB);
           }
         }
@@ -366,26 +370,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
         const uint64_t a_hi = a_const | (uint64_t)(smem_u32(a_base + (size_t)sa * 2 * a_plane) >> 4);
         const uint64_t a_lo = a_hi + (a_plane >> 4);
         uint32_t row_off = 0;
-        for (int tap = 0; tap < p.taps; tap++, rb.advance(SB), row_off += (uint32_t)p.dil) {
+        for (int tap = 0; tap < p.taps; tap += p.TPS, rb.advance(SB)) {
           const uint32_t sb = rb.idx;
+          const int n = min(p.TPS, p.taps - tap);
           mbar_wait(&fullB[sb], rb.phase);
           tc_fence_after();
           if (leader) {
-            const uint64_t b_hi = b_const | (uint64_t)(smem_u32(b_base + (size_t)sb * 2 * b_plane) >> 4);
-            const uint64_t b_lo = b_hi + (b_plane >> 4);
-            const uint64_t ah0 = a_hi + row_off, al0 = a_lo + row_off;
-            const uint32_t first = (kb | tap) ? 1u : 0u;
-            // consecutive MMAs alternate between tiles / accumulator groups
+            uint64_t b_hi = b_const | (uint64_t)(smem_u32(b_base + (size_t)sb * p.TPS * 2 * b_plane) >> 4);
+            for (int j = 0; j < n; j++, b_hi += (2 * b_plane) >> 4, row_off += (uint32_t)p.dil) {
+              const uint64_t b_lo = b_hi + (b_plane >> 4);
+              const uint64_t ah0 = a_hi + row_off, al0 = a_lo + row_off;
+              const uint32_t first = (kb | tap | j) ? 1u : 0u;
+              // consecutive MMAs alternate between tiles / accumulator groups
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++)            // A_lo * B_hi
-              tc_mma_f16(d0 + mt * tile_cols + g_cross, al0 + mt * 128, b_hi, idesc, first);
+              for (int mt = 0; mt < MT; mt++)          // A_lo * B_hi
+                tc_mma_f16(d0 + mt * tile_cols + g_cross, al0 + mt * 128, b_hi, idesc, first);
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++)            // A_hi * B_hi
-              tc_mma_f16(d0 + mt * tile_cols, ah0 + mt * 128, b_hi, idesc, TG >= 2 ? first : 1u);
+              for (int mt = 0; mt < MT; mt++)          // A_hi * B_hi
+                tc_mma_f16(d0 + mt * tile_cols, ah0 + mt * 128, b_hi, idesc, TG >= 2 ? first : 1u);
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++)            // A_hi * B_lo
-              tc_mma_f16(d0 + mt * tile_cols + g_cross2, ah0 + mt * 128, b_lo, idesc, TG == 3 ? first : 1u);
+              for (int mt = 0; mt < MT; mt++)          // A_hi * B_lo
+                tc_mma_f16(d0 + mt * tile_cols + g_cross2, ah0 + mt * 128, b_lo, idesc, TG == 3 ? first : 1u);
+            }
             tc_commit(&emptyB[sb]);                    // weight stage free once these MMAs retire
+          } else {
+            row_off += (uint32_t)(n * p.dil);
           }
           __syncwarp();
         }
@@ -489,7 +498,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
           mbar_wait(&emptyA[ra.idx], ra.phase ^ 1);
           convert_store(v[d], ra.idx);
           fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(&fullA[ra.idx]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&fullA[ra.idx]);   // one arrival per transform warp
           ra.advance(SA);
           if (wt == 0 && s_kb == KBLOCKS - 1) TC_STAMP(s_il, 1);
           if (++s_kb == KBLOCKS) { s_kb = 0; s_il++; }
@@ -518,7 +528,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
         default: tc_epilogue_item<FS2_ACT_NONE>(p, acc, stage, q, lane, it, inv_ws); break;
       }
       tc_fence_before();
-      mbar_arrive(&accEmpty[buf]);                     // all of this thread's tcgen05.ld of the set have completed
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&accEmpty[buf]);      // this warp's tcgen05.ld of the set have completed
       if (warp == 2 + TC_TW && lane == 0) TC_STAMP((int)itT, 5);
     }
   }
@@ -601,7 +612,12 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.MT = mt; p.R = R;
   p.TG = p.acc_stride <= 32 ? 3 : (p.acc_stride <= 64 ? 2 : 1);   // spread split terms while two sets still fit in 512 columns
   const size_t fixed = 4 * TC_STAGE_FLOATS * sizeof(float) + (2 * TC_SA_MAX + 2 * TC_SB_MAX + 4) * 8 + 16;
-  const size_t a_stage = (size_t)2 * TC_CHUNKS * R * 16, b_stage = (size_t)2 * TC_CHUNKS * p.NB * 16;
+  const size_t tap_bytes = (size_t)2 * TC_CHUNKS * p.NB * 16;
+  int tps = (int)(8192 / tap_bytes);                    // ~8 KB per bulk copy / handshake
+  if (tps < 1) tps = 1;
+  if (tps > a->taps) tps = a->taps;
+  p.TPS = tps;
+  const size_t a_stage = (size_t)2 * TC_CHUNKS * R * 16, b_stage = (size_t)tps * tap_bytes;
   const size_t budget = 226 * 1024;
   const int kblocks = a->Cin / TC_KB;
   int sa = kblocks < 3 ? 2 : 3, sb = TC_SB_MAX;        // prefer deep weight rings (bulk-copy latency), then a third slab stage

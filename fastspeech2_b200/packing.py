@@ -52,7 +52,7 @@ def split_fp16(w: Tensor):
 
 def pack_conv_tc(w: Tensor):
     """[taps][Cin][N] fp32 -> byte buffer for the tcgen05 kernel (see include/fs2b200.h):
-         128-byte header (float32[0] = 1/scale)  |  [N/NB][taps][Cin/16][hi|lo][2 K-chunks][NB][8 halfs]
+         128-byte header (float32[0] = 1/scale)  |  [N/NB][Cin/16][taps][hi|lo][2 K-chunks][NB][8 halfs]
     Every (tap, 16-channel K-block) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major, fp16).
     Returns None when the shape is not served by the tensor-core kernel."""
     taps, cin, n = w.shape
@@ -62,7 +62,7 @@ def pack_conv_tc(w: Tensor):
     hi, lo, s = split_fp16(w)
     both = torch.stack([hi, lo], dim=0)                                  # [2][taps][Cin][N]
     t = both.reshape(2, taps, cin // 16, 2, 8, n // nb, nb)              # [2][tap][kb][chunk][e][nblk][nn]
-    tiles = t.permute(5, 1, 2, 0, 3, 6, 4).contiguous()                  # [nblk][tap][kb][2][chunk][nn][e]
+    tiles = t.permute(5, 2, 1, 0, 3, 6, 4).contiguous()                  # [nblk][kb][tap][2][chunk][nn][e]
     header = torch.zeros(TC_HEADER_BYTES // 4, dtype=torch.float32, device=w.device)
     header[0] = 1.0 / s
     return torch.cat([header.view(torch.uint8), tiles.view(torch.uint8).reshape(-1)])
