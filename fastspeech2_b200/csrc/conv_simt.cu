@@ -5,16 +5,14 @@
 // and is the fallback for shapes the tcgen05 path does not take.  One kernel covers nn.Linear (taps = 1),
 // nn.Conv1d with dilation, and a phase group of ConvTranspose1d (see fs2b200.h).
 //
-// Tiling: CTA = 128 rows (time) x BN output channels, BK = 16, 256 threads, 8 x TN register tile per thread,
+// Tiling: CTA = 128 (or 64, for small problems) rows (time) x BN output channels, BK = 16, 256 threads, TM x TN register tile per thread,
 // A tile transposed into smem so the inner product reads two broadcast float4 (A) and two conflict-free float4 (B)
 // per 64 FMAs; global->register->smem double buffering, one __syncthreads per k-step.
 #include "common.cuh"
 
 namespace fs2 {
 
-constexpr int BM = 128;
 constexpr int BK = 16;
-constexpr int AS_LD = BM + 4;
 
 struct ConvP {
   const float* x; long long xbs, xrs;
@@ -30,8 +28,11 @@ struct ConvP {
   int tiles_per_batch;
 };
 
-template <int BN, int ACT>
+template <int BM, int BN, int ACT>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
+  constexpr int AS_LD = BM + 4;
+  constexpr int TM = BM / 16;              // 8 or 4 rows per thread
+  constexpr int A_PER_THREAD = BM * BK / 4 / 256;   // float4 loads of the A tile per thread (2 or 1)
   constexpr int TN = BN / 16;              // 8, 4 or 2 columns per thread
   constexpr int NG = (TN == 8) ? 2 : 1;    // column groups per thread
   constexpr int GW = (TN == 2) ? 2 : 4;    // group width
@@ -51,13 +52,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
   const int kc = p.Cin / BK;               // k-steps per tap
   const int KT = p.taps * kc;
 
-  float acc[8][NG * GW];
+  float acc[TM][NG * GW];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < TM; i++)
 #pragma unroll
     for (int j = 0; j < NG * GW; j++) acc[i][j] = 0.f;
 
-  float4 ra[2];
+  float4 ra[A_PER_THREAD];
   float4 rb[B_PER_THREAD];
 
   auto load_global = [&](int kt) {
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
     const int c0 = (kt - tap * kc) * BK;
     const int shift = tap * p.dil - p.pad;
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < A_PER_THREAD; i++) {
       const int f = tid + i * 256;
       const int row = f >> 2, c4 = f & 3;
       const int t = t0 + row + shift;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
   };
   auto store_smem = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < A_PER_THREAD; i++) {
       const int f = tid + i * 256;
       const int row = f >> 2, c4 = f & 3;
       As[buf][c4 * 4 + 0][row] = ra[i].x;
@@ -123,9 +124,15 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
     if (kt + 1 < KT) load_global(kt + 1);
 #pragma unroll
     for (int k = 0; k < BK; k++) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float av[TM];
+      {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+        if constexpr (TM == 8) {
+          const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+          av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+        }
+      }
       float bv[NG * GW];
       if constexpr (TN == 2) {
         const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < TM; i++)
 #pragma unroll
         for (int j = 0; j < NG * GW; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
   // ---- epilogue: bias, activation, residual, alpha/accumulate, row mask ----
   const int len_b = p.row_lens ? p.row_lens[b] : p.T;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < TM; i++) {
     const int m = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
     const int t = t0 + m;
     if (t >= p.T) continue;
@@ -199,17 +206,23 @@ int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s) {
   p.alpha = a->alpha; p.accumulate = a->accumulate;
   p.row_lens = a->row_lens;
   p.y = a->y; p.ybs = a->y_batch_stride; p.yrs = a->y_row_stride;
-  p.tiles_per_batch = (a->T + BM - 1) / BM;
+  // 128-row tiles by default; 64-row tiles when the grid would not even give every SM two CTAs (encoder / predictors: 2048 rows)
+  const int nblk = a->N > 64 ? (a->N + 127) / 128 : 1;
+  const bool small = (long long)((a->T + 127) / 128) * a->B * nblk < 2LL * 148;
+  const int bm = small ? 64 : 128;
+  p.tiles_per_batch = (a->T + bm - 1) / bm;
   const long long gx = (long long)p.tiles_per_batch * a->B;
   if (gx > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   prof_before(s);
-#define FS2_SIMT_LAUNCH(BN_, grid_)                                                                   \
-  switch (a->out_act) {                                                                               \
-    case FS2_ACT_RELU: conv_simt_kernel<BN_, FS2_ACT_RELU><<<grid_, 256, 0, s>>>(p); break;           \
-    case FS2_ACT_TANH: conv_simt_kernel<BN_, FS2_ACT_TANH><<<grid_, 256, 0, s>>>(p); break;           \
-    case FS2_ACT_LRELU: conv_simt_kernel<BN_, FS2_ACT_LRELU><<<grid_, 256, 0, s>>>(p); break;         \
-    default: conv_simt_kernel<BN_, FS2_ACT_NONE><<<grid_, 256, 0, s>>>(p); break;                     \
+#define FS2_SIMT_ACT(BM_, BN_, grid_)                                                                      \
+  switch (a->out_act) {                                                                                    \
+    case FS2_ACT_RELU: conv_simt_kernel<BM_, BN_, FS2_ACT_RELU><<<grid_, 256, 0, s>>>(p); break;           \
+    case FS2_ACT_TANH: conv_simt_kernel<BM_, BN_, FS2_ACT_TANH><<<grid_, 256, 0, s>>>(p); break;           \
+    case FS2_ACT_LRELU: conv_simt_kernel<BM_, BN_, FS2_ACT_LRELU><<<grid_, 256, 0, s>>>(p); break;         \
+    default: conv_simt_kernel<BM_, BN_, FS2_ACT_NONE><<<grid_, 256, 0, s>>>(p); break;                     \
   }
+#define FS2_SIMT_LAUNCH(BN_, grid_)                   \
+  if (small) { FS2_SIMT_ACT(64, BN_, grid_) } else { FS2_SIMT_ACT(128, BN_, grid_) }
   if (a->N > 64) {
     dim3 grid((unsigned)gx, (a->N + 127) / 128);
     FS2_SIMT_LAUNCH(128, grid)
@@ -221,6 +234,7 @@ int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s) {
     FS2_SIMT_LAUNCH(32, grid)
   }
 #undef FS2_SIMT_LAUNCH
+#undef FS2_SIMT_ACT
   prof_after(s, 0, 2.0 * a->B * a->T * (double)a->Cin * a->taps * a->N);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
