@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS, MAX_POSTNET, MAX_STAGES, MAX_RESBLOCKS, MAX_DIL = 12, 8, 8, 32, 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
@@ -41,7 +41,7 @@ class LayerNormArgs(C.Structure):
 
 class AttentionArgs(C.Structure):
     _fields_ = [("qkv", fp), ("ctx", fp), ("B", i32), ("T", i32), ("H", i32), ("Dh", i32),
-                ("key_lens", fp), ("scale", f32)]
+                ("key_lens", fp), ("scale", f32), ("backend", i32), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class EmbedArgs(C.Structure):
@@ -142,6 +142,7 @@ EXPORTS = {
     "fs2_conv_tc_block": (i32, [i32]),
     "fs2_layernorm": (i32, [C.POINTER(LayerNormArgs), fp]),
     "fs2_attention": (i32, [C.POINTER(AttentionArgs), fp]),
+    "fs2_attention_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
     "fs2_embed_positions": (i32, [C.POINTER(EmbedArgs), fp]),
     "fs2_add_speaker": (i32, [C.POINTER(RowBiasArgs), fp]),
     "fs2_variance_head": (i32, [C.POINTER(VarianceHeadArgs), fp]),

@@ -49,6 +49,7 @@ struct TcP {
   const float* x; long long xbs, xrs;
   int B, T, Cin;
   const float* wt;                 // tiled weights, see packing.pack_conv_tc
+  long long wt_bstride;            // bytes between the tile buffers of consecutive utterances (0 = shared weights)
   const float* bias;
   int N;                           // total output channels
   int NB;                          // output channels per work item (MMA N), N % NB == 0, NB % 16 == 0, NB <= 128
@@ -325,7 +326,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       const int per_blk = p.B * p.tiles_per_batch;
       int nblk = (int)blockIdx.x / per_blk, rem = (int)blockIdx.x - nblk * per_blk;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + TC_HDR + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
+        const long long wb = p.wt_bstride ? (long long)(rem / p.tiles_per_batch) * p.wt_bstride : 0;
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + wb + TC_HDR + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
         const unsigned char* src = wsrc;           // tiles are ordered [kb][tap]: the taps of one K-block are contiguous
         for (int kb = 0; kb < KBLOCKS; kb++) {
           for (int tap = 0; tap < p.taps; tap += p.TPS) {
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     float* stage = stage_all + (warp - 2 - TC_TW) * TC_STAGE_FLOATS;
-    const float inv_ws = __ldg(p.wt);                  // header: 1 / (power-of-two weight scale)
+    const float inv_ws = __ldg(p.wt);                  // header: 1 / (power-of-two weight scale); identical for every utterance
     uint32_t itT = 0;
     Ring rt;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
@@ -572,7 +574,7 @@ bool conv_tc_supported(const fs2_conv1d_args* a) {
 static int g_num_sms = 0;
 
 // `wt` must be the tiled layout produced by fastspeech2_b200.packing.pack_conv_tc (see fs2b200.h)
-int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s) {
+int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s, long long wt_batch_stride) {
   if (!a || !a->x || !wt || !a->y) return FS2_ERR_ARG;
   if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
   if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
@@ -593,7 +595,7 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   TcP p;
   p.x = a->x; p.xbs = a->x_batch_stride; p.xrs = a->x_row_stride;
   p.B = a->B; p.T = a->T; p.Cin = a->Cin;
-  p.wt = wt; p.bias = a->bias; p.N = a->N; p.NB = conv_tc_nb(a->N);
+  p.wt = wt; p.wt_bstride = wt_batch_stride; p.bias = a->bias; p.N = a->N; p.NB = conv_tc_nb(a->N);
   p.taps = a->taps; p.dil = a->dilation; p.pad = a->pad_left;
   p.in_act = a->in_act; p.in_slope = a->in_slope; p.out_act = a->out_act; p.out_slope = a->out_slope;
   p.res = a->res; p.rbs = a->res_batch_stride; p.rrs = a->res_row_stride;

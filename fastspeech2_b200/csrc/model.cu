@@ -30,7 +30,9 @@ void prof_after(cudaStream_t s, int cls, double flops) {
 
 // kernels / launchers defined in the other translation units
 int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s);
-int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s);
+int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s, long long wt_batch_stride = 0);
+int attention_gemm(const fs2_attention_args* a, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t attention_gemm_workspace(int B, int T, int H);
 bool conv_tc_supported(const fs2_conv1d_args* a);
 int conv_tc_nb(int N);
 extern long long* g_tc_trace;
@@ -89,7 +91,7 @@ static int ln(cudaStream_t s, const float* x, float* y, int B, int T, int C, con
   return layernorm(&a, s);
 }
 
-struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; };
+struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; void* att_ws; size_t att_bytes; };
 
 // One FFT block in place on bufs.x  (transformer/Layers.py:21-30)
 static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_block_weights& w, const FftBufs& f, int B, int T,
@@ -97,8 +99,14 @@ static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_
   const int D = m->d_model, F = m->d_inner;
   const float* none = nullptr;
   FS2_TRY(conv(s, f.x, B, T, D, w.w_qkv, tc ? w.w_qkv_tc : none, w.b_qkv, 3 * D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.qkv));
-  fs2_attention_args at{f.qkv, f.ctx, B, T, m->n_head, D / m->n_head, lens, 1.0f / sqrtf((float)(D / m->n_head))};
-  FS2_TRY(attention_simt(&at, s));
+  fs2_attention_args at{};
+  at.qkv = f.qkv; at.ctx = f.ctx; at.B = B; at.T = T; at.H = m->n_head; at.Dh = D / m->n_head; at.key_lens = lens;
+  at.scale = 1.0f / sqrtf((float)(D / m->n_head));
+  if (tc && f.att_ws && T >= 192) {                    // tensor-core path: S = QK^T and PV as split-FP16 GEMMs
+    FS2_TRY(attention_gemm(&at, f.att_ws, f.att_bytes, s));
+  } else {
+    FS2_TRY(attention_simt(&at, s));
+  }
   FS2_TRY(conv(s, f.ctx, B, T, D, w.w_o, tc ? w.w_o_tc : none, w.b_o, D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.tmp, f.x));
   FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln1_g, w.ln1_b, lens));
   FS2_TRY(conv(s, f.x, B, T, D, w.w_1, tc ? w.w_1_tc : none, w.b_1, F, m->k1, 1, (m->k1 - 1) / 2, FS2_ACT_RELU, 0.f, f.hid));
@@ -113,8 +121,13 @@ static bool model_ok(const fs2_acoustic_model* m) {
          m->n_mel > 0 && m->vp_filter > 0;
 }
 
-static FftBufs fft_bufs(Arena& ar, const fs2_acoustic_model* m, size_t rows) {
+static FftBufs fft_bufs(Arena& ar, const fs2_acoustic_model* m, size_t rows, int B = 0, int T = 0, bool tc_attention = false) {
   FftBufs f;
+  f.att_ws = nullptr; f.att_bytes = 0;
+  if (tc_attention && T >= 192) {
+    f.att_bytes = attention_gemm_workspace(B, T, m->n_head);
+    f.att_ws = ar.take(f.att_bytes);
+  }
   f.x = ar.f32(rows * m->d_model);
   f.tmp = ar.f32(rows * m->d_model);
   f.qkv = ar.f32(rows * 3 * m->d_model);
@@ -180,13 +193,13 @@ static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cu
 static int decode_impl(const fs2_acoustic_model* m, const fs2_decode_args* a, cudaStream_t s, Arena& ar) {
   const int B = a->B, T = a->T, D = m->d_model;
   const size_t rows = (size_t)B * T;
-  FftBufs f = fft_bufs(ar, m, rows);
+  FftBufs f = fft_bufs(ar, m, rows, B, T, (m->tc_mask & FS2_TC_DECODER) != 0);
   int pc = 0;
   for (int i = 0; i < m->n_postnet; i++) pc = pc > m->post_cout[i] ? pc : m->post_cout[i];
   float* pa = ar.f32(rows * pc);
   float* pb = ar.f32(rows * pc);
   if (ar.dry) return FS2_OK;
-  if (!f.x || !f.tmp || !f.qkv || !f.ctx || !f.hid || !pa || !pb) return FS2_ERR_WORKSPACE;
+  if (!f.x || !f.tmp || !f.qkv || !f.ctx || !f.hid || !pa || !pb || (f.att_bytes && !f.att_ws)) return FS2_ERR_WORKSPACE;
   if (T > m->dec_pos_rows) return FS2_ERR_ARG;
 
   fs2_length_regulate_args lr{a->x_adapted, a->cum_dur, m->dec_pos, f.x, B, a->L, T, D};
@@ -282,7 +295,7 @@ using namespace fs2;
 
 extern "C" {
 
-int fs2_abi_version(void) { return 2; }
+int fs2_abi_version(void) { return 3; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count; }
 size_t fs2_struct_size(int which) {
@@ -332,7 +345,11 @@ const char* fs2_build_info(void) { return "fs2b200 sm_100a (tcgen05 3xTF32 conv 
 
 int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t st) { return conv1d_dispatch(a, S(st)); }
 int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t st) { return layernorm(a, S(st)); }
-int fs2_attention(const fs2_attention_args* a, fs2_stream_t st) { return attention_simt(a, S(st)); }
+int fs2_attention(const fs2_attention_args* a, fs2_stream_t st) {
+  if (a && a->backend == 1) return attention_gemm(a, a->workspace, a->workspace_bytes, S(st));
+  return attention_simt(a, S(st));
+}
+size_t fs2_attention_workspace_bytes(int B, int T, int H) { return (B > 0 && T > 0 && H > 0) ? attention_gemm_workspace(B, T, H) : 0; }
 int fs2_embed_positions(const fs2_embed_args* a, fs2_stream_t st) { return embed_positions(a, S(st)); }
 int fs2_add_speaker(const fs2_rowbias_args* a, fs2_stream_t st) { return add_speaker(a, S(st)); }
 int fs2_variance_head(const fs2_variance_head_args* a, fs2_stream_t st) { return variance_head(a, S(st)); }

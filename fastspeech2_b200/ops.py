@@ -49,13 +49,17 @@ def layernorm(x, gamma, beta, row_lens=None, eps=1e-5):
     return y
 
 
-def attention(qkv, n_head, key_lens=None):
+def attention(qkv, n_head, key_lens=None, backend=0):
     _need_cuda(qkv)
     B, T, D3 = qkv.shape
     D = D3 // 3
     ctx = torch.empty(B, T, D, dtype=torch.float32, device=qkv.device)
+    ws = None
+    if backend == 1:
+        ws = torch.empty(L.lib().fs2_attention_workspace_bytes(B, T, n_head), dtype=torch.uint8, device=qkv.device)
     a = L.AttentionArgs(qkv=qkv.data_ptr(), ctx=ctx.data_ptr(), B=B, T=T, H=n_head, Dh=D // n_head, key_lens=L.ptr(key_lens),
-                        scale=float((D // n_head) ** -0.5))
+                        scale=float((D // n_head) ** -0.5), backend=backend, workspace=L.ptr(ws),
+                        workspace_bytes=0 if ws is None else ws.numel())
     L.check(L.lib().fs2_attention(C.byref(a), _stream(qkv.device)), "fs2_attention")
     return ctx
 

@@ -46,10 +46,11 @@ enum { FS2_CONV_AUTO = 0, FS2_CONV_SIMT = 1, FS2_CONV_TC = 2 };
 /* which parts of the acoustic model may use the 3xTF32 tensor-core kernel (fs2_acoustic_model.tc_mask) */
 enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POSTNET = 8 };
 
-/* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per CTA,
- * hi = w & 0xffffe000 (a TF32 value), lo = w - hi, the tiled buffer is
- *     [N/NB][taps][Cin/16][2: hi,lo][4: 16-byte K chunk][NB][4 floats]
- * i.e. every (tap, 16-channel K-block) stage is one contiguous 128*NB-byte smem image (UMMA no-swizzle K-major). */
+/* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per work item,
+ * s = a per-layer power of two, hi = fp16(s*w), lo = fp16(s*w - hi), the tiled byte buffer is
+ *     128-byte header (float32[0] = 1/s)  |  [N/NB][Cin/16][taps][2: hi,lo][2: 16-byte K chunk][NB][8 halfs]
+ * i.e. every (K-block, tap) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major, fp16), fetched by one
+ * cp.async.bulk.  fastspeech2_b200/packing.py::pack_conv_tc builds it. */
 int fs2_conv_tc_block(int N); /* 0 when N is not supported by the tensor-core kernel */
 
 #define FS2_MAX_LAYERS 12
@@ -96,8 +97,11 @@ int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t stream);
 typedef struct fs2_attention_args {
   const float* qkv; float* ctx; int B, T, H, Dh;
   const int32_t* key_lens; float scale;
+  int backend;                  /* 0 = exact fp32 flash-style kernel; 1 = tensor-core path (split-FP16 GEMMs + row softmax), needs workspace */
+  void* workspace; size_t workspace_bytes;   /* backend 1 only: >= fs2_attention_workspace_bytes(B, T, H) */
 } fs2_attention_args;
 int fs2_attention(const fs2_attention_args* a, fs2_stream_t stream);
+size_t fs2_attention_workspace_bytes(int B, int T, int H);
 
 /* y[b,l,:] = table[ids[b,l]] + pos[l]   (+ spk[speakers[b]] when spk != NULL: not used by the encoder, kept for tests) */
 typedef struct fs2_embed_args {

@@ -100,6 +100,20 @@ def test_attention(T, lens):
     assert (got.cpu() - want).abs().max() < 5e-6
 
 
+@pytest.mark.parametrize("T,lens", [(300, [300, 129, 1]), (1000, [1000, 777, 513]), (1100, [1100, 64, 1037])])
+def test_attention_tensor_core_path(T, lens):
+    """S = QK^T / PV as split-FP16 tcgen05 GEMMs + row softmax (decoder path): fp32-class accuracy expected."""
+    qkv = rnd(3, T, 768, seed=2)
+    kl = torch.tensor(lens, dtype=torch.int32)
+    want = E.attention(qkv.double(), 2, kl)
+    got = ops.attention(qkv.to(DEV), 2, kl.to(DEV), backend=1)
+    exact = ops.attention(qkv.to(DEV), 2, kl.to(DEV), backend=0)
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - want).abs().max().item()
+    err0 = (exact.cpu().double() - want).abs().max().item()
+    assert err < 2e-5, (err, err0)
+
+
 def test_embed_and_speaker():
     table = rnd(361, 256, seed=1)
     pos = rnd(1001, 256, seed=2)
