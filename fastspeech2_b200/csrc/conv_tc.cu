@@ -35,7 +35,7 @@ namespace fs2 {
 
 constexpr int TC_KB = 16;          // input channels per K-block (one K=16 FP16 MMA per split term)
 constexpr int TC_CHUNKS = TC_KB / 8;  // 16-byte K-chunks (8 halfs) per K-block
-constexpr int TC_SA_MAX = 4;       // activation slab stages (runtime p.SA)
+constexpr int TC_SA_MAX = 8;       // activation slab stages (runtime p.SA)
 constexpr int TC_SB_MAX = 8;       // weight stages (runtime p.SB)
 constexpr int TC_TW = 8;            // transform warps
 constexpr int TC_TTHREADS = TC_TW * 32;
@@ -572,6 +572,7 @@ bool conv_tc_supported(const fs2_conv1d_args* a) {
 }
 
 static int g_num_sms = 0;
+int g_tc_tune[4] = {0, 0, 0, 0};   // debug overrides: SA, SB, TPS, grid (0 = heuristic); set through fs2_debug_set_tc_tuning
 
 // `wt` must be the tiled layout produced by fastspeech2_b200.packing.pack_conv_tc (see fs2b200.h)
 int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s, long long wt_batch_stride) {
@@ -615,19 +616,24 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.TG = p.acc_stride <= 32 ? 3 : (p.acc_stride <= 64 ? 2 : 1);   // spread split terms while two sets still fit in 512 columns
   const size_t fixed = 4 * TC_STAGE_FLOATS * sizeof(float) + (2 * TC_SA_MAX + 2 * TC_SB_MAX + 4) * 8 + 16;
   const size_t tap_bytes = (size_t)2 * TC_CHUNKS * p.NB * 16;
-  int tps = (int)(8192 / tap_bytes);                    // ~8 KB per bulk copy / handshake
-  if (tps < 1) tps = 1;
+  // Taps per weight stage: measured (scripts/tc_tune.py, profiles/r01_tc_tune.txt) -- grouping 4 taps per bulk copy / handshake
+  // is 10-25 % faster for the k = 5..11 layers at every channel width; k <= 3 layers are best with one tap per stage.
+  int tps = a->taps >= 5 ? 4 : 1;
+  if (g_tc_tune[2] > 0) tps = g_tc_tune[2];
   if (tps > a->taps) tps = a->taps;
   p.TPS = tps;
   const size_t a_stage = (size_t)2 * TC_CHUNKS * R * 16, b_stage = (size_t)tps * tap_bytes;
   const size_t budget = 226 * 1024;
   const int kblocks = a->Cin / TC_KB;
-  int sa = kblocks < 3 ? 2 : 3, sb = TC_SB_MAX;        // prefer deep weight rings (bulk-copy latency), then a third slab stage
+  int sa = kblocks < 3 ? 2 : 3, sb = tps > 1 ? 4 : TC_SB_MAX;   // ring depths matter little (measured); keep both rings >= 2-3 deep
   while (fixed + sa * a_stage + sb * b_stage > budget && sb > 3) sb--;
   while (fixed + sa * a_stage + sb * b_stage > budget && sa > 2) sa--;
   while (fixed + sa * a_stage + sb * b_stage > budget && sb > 2) sb--;
   if (fixed + sa * a_stage + sb * b_stage > budget) return FS2_ERR_UNSUPPORTED;
-  if (sa < TC_SA_MAX && kblocks >= 4 && fixed + (sa + 1) * a_stage + sb * b_stage <= budget) sa++;
+  if (sa < 4 && kblocks >= 4 && fixed + (sa + 1) * a_stage + sb * b_stage <= budget) sa++;
+  if (g_tc_tune[0] > 0) sa = g_tc_tune[0] > TC_SA_MAX ? TC_SA_MAX : g_tc_tune[0];
+  if (g_tc_tune[1] > 0) sb = g_tc_tune[1] > TC_SB_MAX ? TC_SB_MAX : g_tc_tune[1];
+  if (fixed + sa * a_stage + sb * b_stage > budget) return FS2_ERR_UNSUPPORTED;
   p.SA = sa; p.SB = sb;
   const size_t smem = fixed + sa * a_stage + sb * b_stage;
   p.tmem_cols = pow2_cols(2 * mt * p.TG * p.acc_stride);
@@ -635,7 +641,8 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   const long long n_items = (long long)(a->N / p.NB) * a->B * p.tiles_per_batch;
   if (n_items > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   p.n_items = (int)n_items;
-  const int grid = n_items < g_num_sms ? (int)n_items : g_num_sms;
+  int grid = n_items < g_num_sms ? (int)n_items : g_num_sms;
+  if (g_tc_tune[3] > 0 && g_tc_tune[3] < grid) grid = g_tc_tune[3];
   prof_before(s);
 #define FS2_TC_LAUNCH(MT_, TG_) conv_tc_kernel<MT_, TG_><<<grid, TC_THREADS, smem, s>>>(p)
   if (mt == 2) {
