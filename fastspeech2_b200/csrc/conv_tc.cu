@@ -194,7 +194,23 @@ __device__ __forceinline__ float tc_act(float v, float slope) {
 template <int ACT, int W, bool FULL>
 __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, float* stage, int lane, float* yptr, const float* rptr,
                                                   const float* bias, int rows_live, int rows_valid, float inv_ws) {
-  constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+  constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI, HALF = ITERS / 2;
+  const int rr = lane / LPR;
+  const long long ystep = (long long)RPI * p.yrs, rstep = (long long)RPI * p.rrs;
+  // Residual loads are software-pipelined by half-blocks: the first half is requested before the TMEM load / transpose, the
+  // second half before the first half is consumed (variant bit 8 restores the late, unpipelined loads for A/B runs).
+  float4 r0[HALF], r1[HALF];
+#pragma unroll
+  for (int k = 0; k < HALF; k++) {
+    r0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    r1[k] = r0[k];
+  }
+  const bool early = rptr != nullptr && !(p.variant & 8u);
+  if (early) {
+#pragma unroll
+    for (int k = 0; k < HALF; k++)
+      if (FULL || k * RPI + rr < rows_valid) r0[k] = *reinterpret_cast<const float4*>(rptr + k * rstep);
+  }
   {
     uint32_t v[32];
     if (W == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
@@ -210,25 +226,32 @@ __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, 
           make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]), __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
   }
   __syncwarp();
-  const int rr = lane / LPR;
   const float slope = p.out_slope, alpha = p.alpha;
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias));
-  const long long ystep = (long long)RPI * p.yrs, rstep = (long long)RPI * p.rrs;
-  constexpr int HALF = ITERS / 2;
 #pragma unroll
-  for (int h = 0; h < 2; h++) {                        // two half-blocks: bounds the registers held by in-flight loads
-    float4 rv[HALF], yv[HALF];
-#pragma unroll
-    for (int k = 0; k < HALF; k++) {
-      rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      yv[k] = rv[k];
-    }
+  for (int h = 0; h < 2; h++) {
+    float4 (&rv)[HALF] = h == 0 ? r0 : r1;
     if (rptr) {
+      if (h == 0) {
+        if (early) {                                   // request the second half now; it lands while the first half is processed
 #pragma unroll
-      for (int k = 0; k < HALF; k++)
-        if (FULL || (h * HALF + k) * RPI + rr < rows_valid) rv[k] = *reinterpret_cast<const float4*>(rptr + (h * HALF + k) * rstep);
+          for (int k = 0; k < HALF; k++)
+            if (FULL || (HALF + k) * RPI + rr < rows_valid) r1[k] = *reinterpret_cast<const float4*>(rptr + (HALF + k) * rstep);
+        } else {
+#pragma unroll
+          for (int k = 0; k < HALF; k++)
+            if (FULL || k * RPI + rr < rows_valid) r0[k] = *reinterpret_cast<const float4*>(rptr + k * rstep);
+        }
+      } else if (!early) {
+#pragma unroll
+        for (int k = 0; k < HALF; k++)
+          if (FULL || (HALF + k) * RPI + rr < rows_valid) r1[k] = *reinterpret_cast<const float4*>(rptr + (HALF + k) * rstep);
+      }
     }
+    float4 yv[HALF];
+#pragma unroll
+    for (int k = 0; k < HALF; k++) yv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.accumulate) {
 #pragma unroll
       for (int k = 0; k < HALF; k++)
