@@ -437,13 +437,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const int items = rows_needed * TC_CHUNKS;
     // Register ring of TC_DEPTH K-blocks: the loads of K-block seq + TC_DEPTH (possibly of a later work item) are issued as
     // soon as K-block seq has been converted and stored, so ~TC_DEPTH slabs of loads stay in flight per SM.
-    float4 v[TC_DEPTH][TC_LD][2];
+    constexpr int LD = MT == 4 ? 5 : TC_LD;           // (row, chunk) items per thread per K-block
+    constexpr int DEPTH = MT == 4 ? 2 : TC_DEPTH;     // K-blocks in flight (register ring)
+    float4 v[DEPTH][LD][2];
     const bool lrelu_in = p.in_act == FS2_ACT_LRELU;
     const float in_slope = p.in_slope;
     // per-thread (row, chunk) slots: fixed for the whole kernel
-    int rowu[TC_LD], offu[TC_LD];
+    int rowu[LD], offu[LD];
 #pragma unroll
-    for (int u = 0; u < TC_LD; u++) {
+    for (int u = 0; u < LD; u++) {
       const int idx = u * TC_TTHREADS + wt;
       rowu[u] = idx < items ? (idx >> 1) : -1;
       offu[u] = (((idx & 1) * R) + (idx >> 1)) * 16;
@@ -460,10 +462,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       }
     };
     l_set_item();
-    auto issue_loads = [&](float4 (&dst)[TC_LD][2]) {   // loads K-block (l_item, l_kb), then advances the load cursor
+    auto issue_loads = [&](float4 (&dst)[LD][2]) {   // loads K-block (l_item, l_kb), then advances the load cursor
       const float* xk = l_xb + l_kb * TC_KB;
 #pragma unroll
-      for (int u = 0; u < TC_LD; u++) {
+      for (int u = 0; u < LD; u++) {
         const int t = l_tfirst + rowu[u];
         dst[u][0] = make_float4(0.f, 0.f, 0.f, 0.f);
         dst[u][1] = dst[u][0];
@@ -475,11 +477,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       }
       if (++l_kb == KBLOCKS) { l_kb = 0; l_item += gridDim.x; l_set_item(); }
     };
-    auto convert_store = [&](const float4 (&src)[TC_LD][2], uint32_t sa) {
+    auto convert_store = [&](const float4 (&src)[LD][2], uint32_t sa) {
       unsigned char* hi = a_base + (size_t)sa * 2 * a_plane;
       unsigned char* lo = hi + a_plane;
 #pragma unroll
-      for (int u = 0; u < TC_LD; u++) {
+      for (int u = 0; u < LD; u++) {
         if (rowu[u] < 0) continue;
         const float f[8] = {src[u][0].x, src[u][0].y, src[u][0].z, src[u][0].w, src[u][1].x, src[u][1].y, src[u][1].z, src[u][1].w};
         uint32_t hw[4], lw[4];
@@ -510,13 +512,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total = my_items * KBLOCKS;
 #pragma unroll
-    for (int d = 0; d < TC_DEPTH; d++)
+    for (int d = 0; d < DEPTH; d++)
       if (d < total) issue_loads(v[d]);
     Ring ra;
     int s_kb = 0, s_il = 0;                            // store cursor (for the debug timeline only)
-    for (int base = 0; base < total; base += TC_DEPTH) {
+    for (int base = 0; base < total; base += DEPTH) {
 #pragma unroll
-      for (int d = 0; d < TC_DEPTH; d++) {
+      for (int d = 0; d < DEPTH; d++) {
         const int seq = base + d;
         if (seq < total) {
           if (wt == 0 && s_kb == 0) TC_STAMP(s_il, 0);
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
           ra.advance(SA);
           if (wt == 0 && s_kb == KBLOCKS - 1) TC_STAMP(s_il, 1);
           if (++s_kb == KBLOCKS) { s_kb = 0; s_il++; }
-          if (seq + TC_DEPTH < total) issue_loads(v[d]);
+          if (seq + DEPTH < total) issue_loads(v[d]);
         }
       }
     }
@@ -614,6 +616,8 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e != cudaSuccess) { g_num_sms = 0; return FS2_ERR_CUDA - (int)e; }
   }
   TcP p;
@@ -630,13 +634,16 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.acc_stride = (p.NB + 31) & ~31;
   const int halo = (a->taps - 1) * a->dilation;
   const int tiles128 = (a->T + 127) / 128;
-  int mt = 2;                                          // two accumulator sets of MT tiles: 2*MT*acc_stride <= 512 columns
-  if (mt > tiles128) mt = tiles128;
-  if (mt * 128 + halo > TC_LD * TC_TTHREADS / TC_CHUNKS) mt = 1;   // rows one register-ring slot can hold
+  int mt = 2;                                          // two accumulator sets of MT tiles: 2*MT*TG*acc_stride <= 512 columns
+  if (p.acc_stride <= 64 && tiles128 >= 4 && 4 * 128 + halo <= 5 * TC_TTHREADS / TC_CHUNKS) mt = 4;   // narrow layers: amortise per-item handshakes
+  if (g_tc_tune[3] == -1) mt = 2;                      // debug: force MT = 2
+  if (mt > tiles128) mt = tiles128 >= 2 ? 2 : 1;
+  if (mt == 2 && mt * 128 + halo > TC_LD * TC_TTHREADS / TC_CHUNKS) mt = 1;   // rows one register-ring slot can hold
   int R = mt * 128 + halo;
   R += (12 - (R & 7)) & 7;                             // R % 8 == 4: conflict-free transform stores (2 chunks per row)
   p.MT = mt; p.R = R;
   p.TG = p.acc_stride <= 32 ? 3 : (p.acc_stride <= 64 ? 2 : 1);   // spread split terms while two sets still fit in 512 columns
+  if (mt == 4) p.TG = p.acc_stride <= 32 ? 2 : 1;
   const size_t fixed = 4 * TC_STAGE_FLOATS * sizeof(float) + (2 * TC_SA_MAX + 2 * TC_SB_MAX + 4) * 8 + 16;
   const size_t tap_bytes = (size_t)2 * TC_CHUNKS * p.NB * 16;
   // Taps per weight stage: measured (scripts/tc_tune.py, profiles/r01_tc_tune.txt) -- grouping 4 taps per bulk copy / handshake
@@ -668,7 +675,9 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   if (g_tc_tune[3] > 0 && g_tc_tune[3] < grid) grid = g_tc_tune[3];
   prof_before(s);
 #define FS2_TC_LAUNCH(MT_, TG_) conv_tc_kernel<MT_, TG_><<<grid, TC_THREADS, smem, s>>>(p)
-  if (mt == 2) {
+  if (mt == 4) {
+    if (p.TG == 2) FS2_TC_LAUNCH(4, 2); else FS2_TC_LAUNCH(4, 1);
+  } else if (mt == 2) {
     if (p.TG == 3) FS2_TC_LAUNCH(2, 3); else if (p.TG == 2) FS2_TC_LAUNCH(2, 2); else FS2_TC_LAUNCH(2, 1);
   } else {
     if (p.TG == 3) FS2_TC_LAUNCH(1, 3); else if (p.TG == 2) FS2_TC_LAUNCH(1, 2); else FS2_TC_LAUNCH(1, 1);
