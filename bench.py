@@ -189,7 +189,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = _lib.lib()
 
     pc, mc = configs.make_configs("LJSpeech", tempfile.mkdtemp())
@@ -208,9 +209,13 @@ def run_ours(args):
     spk_h, texts_h, lens_h = spk_h.pin_memory(), texts_h.pin_memory(), lens_h.pin_memory()
     spk, texts, lens = spk_h.to(dev), texts_h.to(dev), lens_h.to(dev)
 
-    def step_device():
+    def step_local():                               # no collectives: safe to run on a single rank
         out = model(spk, texts, lens, L)
         wav = voc(out[1].transpose(1, 2))
+        return out, wav
+
+    def step_device():
+        out, wav = step_local()
         if world > 1:
             gather_padded(wav[:, 0], out[9])
         return out, wav
@@ -282,7 +287,7 @@ def run_ours(args):
     roof = None
     if rank == 0:
         lib.fs2_profile_begin()
-        step_device()
+        step_local()                                # rank 0 only: must not contain a collective
         torch.cuda.synchronize()
         ms = (C.c_double * 4)(); fl = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
         lib.fs2_profile_end(ms, fl, cnt)
