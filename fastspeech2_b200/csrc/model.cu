@@ -343,7 +343,7 @@ int fs2_profile_end(double* ms, double* flops, int64_t* launches) {
   g_prof.clear();
   return rc;
 }
-const char* fs2_build_info(void) { return "fs2b200 sm_100a (tcgen05 3xTF32 conv + fp32 CUDA-core kernels), built " __DATE__ " " __TIME__; }
+const char* fs2_build_info(void) { return "fs2b200 sm_100a (tcgen05 split-FP16 conv + attention GEMMs, fp32 CUDA-core kernels), built " __DATE__ " " __TIME__; }
 
 int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t st) { return conv1d_dispatch(a, S(st)); }
 int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t st) { return layernorm(a, S(st)); }
