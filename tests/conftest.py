@@ -8,6 +8,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_sessionstart(session):
+    # the CPU oracle is ATen: on many-core hosts (the B200 box has 128) more threads than the small test problems can feed is slower
+    import torch
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
     config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference (absent on the GPU box)")

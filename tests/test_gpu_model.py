@@ -56,6 +56,20 @@ def test_fastspeech2_multispeaker_controls(libri_configs, parity_log):
     assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
 
 
+def test_fastspeech2_ragged_multispeaker_long(libri_configs, parity_log):
+    """BASELINE.json configs[3] in miniature: LibriTTS multi-speaker, mixed 64-256 phonemes with padding masks -> T up to ~2000
+    (position table beyond max_seq_len, decoder attention with 2048 padded keys)."""
+    m, sd = _model(libri_configs, seed=13)
+    spk, texts, lens, Lm = synth.make_batch(6, 256, seed=14, n_speakers=904, min_len=64)
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm)
+    out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm)
+    assert torch.equal(out[5].cpu(), ref[5]) and torch.equal(out[9].cpu(), ref[9]) and torch.equal(out[7].cpu(), ref[7])
+    assert int(ref[9].max()) > 1500
+    e = _cmp(out, ref)
+    parity_log("fs2_ragged_libri_B6_L64-256", **e, tmax=int(ref[9].max()))
+    assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
+
+
 def test_fastspeech2_teacher_forced(lj_configs, parity_log):
     m, sd = _model(lj_configs, seed=5)
     spk, texts, lens, Lm = synth.make_batch(4, 48, seed=6, min_len=15)

@@ -52,6 +52,47 @@ def test_conv1d(case):
     assert err < 2e-5, err
 
 
+TC_CASES = [
+    # B, T, Cin, N, taps, dil, pad, in_act, out_act, res, alpha, accumulate, lens      (tcgen05 split-FP16 kernel, backend = 2)
+    (1, 128, 16, 128, 1, 1, 0, 0, 0, False, 1.0, False, False),      # one tile, one K-block (MT = 1)
+    (2, 300, 64, 128, 3, 1, 1, 0, 0, False, 1.0, False, False),      # ragged tail tile (MT = 2)
+    (2, 700, 128, 128, 11, 5, 25, 3, 3, True, 1.0, False, False),    # HiFi-GAN stage-1 conv1 shape: dilation 5, lrelu in/out
+    (2, 520, 256, 256, 7, 1, 3, 0, 0, True, 1.0 / 3, True, False),   # two N-blocks, residual + scaled accumulate
+    (2, 333, 512, 80, 5, 1, 2, 0, 0, True, 1.0, False, False),       # PostNet last conv: N = 80 (16-column tail block)
+    (2, 260, 256, 1024, 9, 1, 4, 0, 1, False, 1.0, False, False),    # conv-FFN w_1 + ReLU, 8 N-blocks
+    (3, 200, 1024, 256, 1, 1, 0, 0, 0, True, 1.0, False, True),      # conv-FFN w_2 + residual + pad-row mask
+    (2, 1500, 32, 32, 3, 3, 3, 3, 3, False, 1.0, False, False),      # 32 channels: MT = 4, two accumulator groups
+    (2, 777, 64, 64, 7, 1, 3, 3, 0, True, 1.0, False, False),        # 64 channels: MT = 4
+    (2, 150, 80, 512, 7, 1, 3, 0, 0, False, 1.0, False, False),      # conv_pre: C_in = 80
+    (2, 257, 64, 64, 2, 1, 1, 3, 0, False, 1.0, False, False),       # ConvTranspose phase group (2 taps)
+    (1, 40, 256, 80, 1, 1, 0, 0, 2, False, 1.0, False, False),       # short sequence, tanh epilogue
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv1d_tensor_core(case):
+    """fs2_conv1d through the tcgen05 kernel against an fp64 evaluation of the same contract.  Error budget: the split
+    keeps 22 bits; what remains is the tensor core's truncating fp32 accumulator (~0.5 ulp per K=16 step)."""
+    B, T, Cin, N, taps, dil, pad, in_act, out_act, use_res, alpha, acc, use_lens = case
+    x = rnd(B, T, Cin, seed=1)
+    w = rnd(taps, Cin, N, seed=2, scale=(taps * Cin) ** -0.5)
+    bias = rnd(N, seed=3, scale=0.1)
+    res = rnd(B, T, N, seed=4) if use_res else None
+    y0 = rnd(B, T, N, seed=5) if acc else None
+    lens = torch.tensor([max(1, T - 7 * (i + 1)) for i in range(B)], dtype=torch.int32) if use_lens else None
+    d = lambda t: None if t is None else t.double()
+    want = E.conv1d(x.double(), w.double(), bias.double(), dil, pad, in_act, 0.1, out_act, 0.1, d(res), alpha, d(y0), lens)
+    wtc = packing.pack_conv_tc(w)
+    assert wtc is not None
+    out = y0.to(DEV).clone() if acc else None
+    got = ops.conv1d(x.to(DEV), w.to(DEV), bias.to(DEV), dilation=dil, pad_left=pad, in_act=in_act, in_slope=0.1, out_act=out_act,
+                     out_slope=0.1, res=None if res is None else res.to(DEV), alpha=alpha, out=out, accumulate=acc,
+                     row_lens=None if lens is None else lens.to(DEV), w_tc=wtc.to(DEV), backend=2)
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - want).abs().max().item()
+    assert err < 6e-5, err
+
+
 def test_conv1d_strided_output_conv_transpose():
     for u, cin, cout, T in ((8, 64, 32, 37), (2, 64, 32, 130)):
         w = rnd(cin, cout, 2 * u, seed=7, scale=0.1)
