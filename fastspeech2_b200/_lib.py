@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LAYERS, MAX_POSTNET, MAX_STAGES, MAX_RESBLOCKS, MAX_DIL = 12, 8, 8, 32, 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
@@ -86,6 +86,7 @@ class AcousticModel(C.Structure):
     _fields_ = [("d_model", i32), ("n_head", i32), ("d_inner", i32), ("k1", i32), ("k2", i32), ("n_enc", i32), ("n_dec", i32),
                 ("n_mel", i32), ("vp_filter", i32), ("vp_kernel", i32), ("n_bins", i32), ("n_vocab", i32), ("n_speakers", i32),
                 ("enc_pos_rows", i32), ("dec_pos_rows", i32), ("tc_mask", i32),
+                ("pitch_frame_level", i32), ("energy_frame_level", i32),
                 ("word_emb", fp), ("enc_pos", fp), ("dec_pos", fp), ("spk_emb", fp),
                 ("enc", FftBlockWeights * MAX_LAYERS), ("dec", FftBlockWeights * MAX_LAYERS),
                 ("dur", PredictorWeights), ("pitch", PredictorWeights), ("energy", PredictorWeights),
@@ -109,6 +110,7 @@ class EncodeArgs(C.Structure):
 
 class DecodeArgs(C.Structure):
     _fields_ = [("B", i32), ("L", i32), ("T", i32), ("x_adapted", fp), ("cum_dur", fp), ("mel_mask_lens", fp),
+                ("p_control", f32), ("p_target_frames", fp), ("e_target_frames", fp), ("p_pred_frames", fp), ("e_pred_frames", fp),
                 ("mel", fp), ("postnet_mel", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
@@ -150,6 +152,7 @@ EXPORTS = {
     "fs2_length_regulate": (i32, [C.POINTER(LengthRegulateArgs), fp]),
     "fs2_conv_post": (i32, [C.POINTER(ConvPostArgs), fp]),
     "fs2_transpose_bct_to_btc": (i32, [fp, fp, i32, i32, i32, fp]),
+    "fs2_add_positions": (i32, [fp, fp, i32, i32, i32, fp]),
     "fs2_encode_workspace_bytes": (C.c_size_t, [C.POINTER(AcousticModel), i32, i32]),
     "fs2_acoustic_encode": (i32, [C.POINTER(AcousticModel), C.POINTER(EncodeArgs), fp]),
     "fs2_decode_workspace_bytes": (C.c_size_t, [C.POINTER(AcousticModel), i32, i32]),

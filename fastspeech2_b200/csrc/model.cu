@@ -54,6 +54,7 @@ int durations(const fs2_durations_args* a, cudaStream_t s);
 int length_regulate(const fs2_length_regulate_args* a, cudaStream_t s);
 int conv_post(const fs2_conv_post_args* a, cudaStream_t s);
 int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t s);
+int add_positions(float* x, const float* pos, int B, int T, int D, cudaStream_t s);
 
 // ------------------------------------------------------------------ workspace bump allocator
 struct Arena {
@@ -137,6 +138,22 @@ static FftBufs fft_bufs(Arena& ar, const fs2_acoustic_model* m, size_t rows, int
   return f;
 }
 
+// VariancePredictor.forward (+ bucketize / embedding add when bins != NULL) on rows [B][T]  (model/modules.py:242-250, :80-100)
+static int run_predictor(cudaStream_t s, const fs2_acoustic_model* m, const fs2_predictor_weights& w, const float* x, int B, int T,
+                         const int32_t* lens, float control, const float* target, const float* bins, const float* emb, float* x_acc,
+                         float* pred_out, float* h1, float* h2) {
+  const int k = m->vp_kernel, D = m->d_model, VF = m->vp_filter;
+  FS2_TRY(conv(s, x, B, T, D, w.w_c1, nullptr, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
+  FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln1_g, w.ln1_b, nullptr));
+  FS2_TRY(conv(s, h2, B, T, VF, w.w_c2, nullptr, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
+  FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln2_g, w.ln2_b, nullptr));
+  fs2_variance_head_args v{};
+  v.h = h2; v.w = w.w_out; v.b = w.b_out; v.B = B; v.L = T; v.C = VF;
+  v.lens = lens; v.control = control; v.target = target;
+  v.bins = bins; v.n_edges = m->n_bins - 1; v.emb = emb; v.D = D; v.x = x_acc; v.pred_out = pred_out;
+  return variance_head(&v, s);
+}
+
 // ------------------------------------------------------------------ phase 1
 static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cudaStream_t s, Arena& ar) {
   const int B = a->B, L = a->L, D = m->d_model, VF = m->vp_filter;
@@ -160,23 +177,18 @@ static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cu
   cudaError_t ce = cudaMemcpyAsync(a->x_adapted, f.x, rows * D * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (ce != cudaSuccess) return FS2_ERR_CUDA - (int)ce;
 
-  auto predictor = [&](const fs2_predictor_weights& w, const float* x, float control, const float* target, const float* bins,
-                       const float* emb, float* pred_out) -> int {
-    const int k = m->vp_kernel;
-    FS2_TRY(conv(s, x, B, L, D, w.w_c1, nullptr, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
-    FS2_TRY(ln(s, h1, h2, B, L, VF, w.ln1_g, w.ln1_b, nullptr));
-    FS2_TRY(conv(s, h2, B, L, VF, w.w_c2, nullptr, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
-    FS2_TRY(ln(s, h1, h2, B, L, VF, w.ln2_g, w.ln2_b, nullptr));
-    fs2_variance_head_args v{};
-    v.h = h2; v.w = w.w_out; v.b = w.b_out; v.B = B; v.L = L; v.C = VF;
-    v.lens = a->src_lens; v.control = control; v.target = target;
-    v.bins = bins; v.n_edges = m->n_bins - 1; v.emb = emb; v.D = D; v.x = a->x_adapted; v.pred_out = pred_out;
-    return variance_head(&v, s);
-  };
   // duration on the un-embedded x; pitch on x; energy on x + pitch embedding.  energy uses p_control (modules.py:124).
-  FS2_TRY(predictor(m->dur, a->x_adapted, 1.f, nullptr, nullptr, nullptr, a->logd_pred));
-  FS2_TRY(predictor(m->pitch, a->x_adapted, a->p_control, a->p_target, m->pitch_bins, m->pitch_emb, a->p_pred));
-  FS2_TRY(predictor(m->energy, a->x_adapted, a->p_control, a->e_target, m->energy_bins, m->energy_emb, a->e_pred));
+  FS2_TRY(run_predictor(s, m, m->dur, a->x_adapted, B, L, a->src_lens, 1.f, nullptr, nullptr, nullptr, a->x_adapted, a->logd_pred, h1, h2));
+  if (!m->pitch_frame_level) {
+    if (!a->p_pred) return FS2_ERR_ARG;
+    FS2_TRY(run_predictor(s, m, m->pitch, a->x_adapted, B, L, a->src_lens, a->p_control, a->p_target, m->pitch_bins, m->pitch_emb,
+                          a->x_adapted, a->p_pred, h1, h2));
+  }
+  if (!m->energy_frame_level) {
+    if (!a->e_pred) return FS2_ERR_ARG;
+    FS2_TRY(run_predictor(s, m, m->energy, a->x_adapted, B, L, a->src_lens, a->p_control, a->e_target, m->energy_bins, m->energy_emb,
+                          a->x_adapted, a->e_pred, h1, h2));
+  }
 
   fs2_durations_args d{};
   d.src = a->d_target ? a->d_target : a->logd_pred; d.use_target = a->d_target != nullptr; d.d_control = a->d_control;
@@ -203,8 +215,25 @@ static int decode_impl(const fs2_acoustic_model* m, const fs2_decode_args* a, cu
   if (!f.x || !f.tmp || !f.qkv || !f.ctx || !f.hid || !pa || !pb || (f.att_bytes && !f.att_ws)) return FS2_ERR_WORKSPACE;
   if (T > m->dec_pos_rows) return FS2_ERR_ARG;
 
-  fs2_length_regulate_args lr{a->x_adapted, a->cum_dur, m->dec_pos, f.x, B, a->L, T, D};
+  const bool frame_level = m->pitch_frame_level || m->energy_frame_level;
+  fs2_length_regulate_args lr{a->x_adapted, a->cum_dur, frame_level ? nullptr : m->dec_pos, f.x, B, a->L, T, D};
   FS2_TRY(length_regulate(&lr, s));
+  if (frame_level) {                                   // frame-level pitch / energy (model/modules.py:139-148), then the position add
+    float* h1 = f.hid;                                 // [rows][d_inner] is free here and d_inner >= 2 * vp_filter is checked below
+    float* h2 = f.hid + rows * m->vp_filter;
+    if ((size_t)m->d_inner < 2 * (size_t)m->vp_filter) return FS2_ERR_UNSUPPORTED;
+    if (m->pitch_frame_level) {
+      if (!a->p_pred_frames) return FS2_ERR_ARG;
+      FS2_TRY(run_predictor(s, m, m->pitch, f.x, B, T, a->mel_mask_lens, a->p_control, a->p_target_frames, m->pitch_bins, m->pitch_emb, f.x,
+                            a->p_pred_frames, h1, h2));
+    }
+    if (m->energy_frame_level) {
+      if (!a->e_pred_frames) return FS2_ERR_ARG;
+      FS2_TRY(run_predictor(s, m, m->energy, f.x, B, T, a->mel_mask_lens, a->p_control, a->e_target_frames, m->energy_bins, m->energy_emb, f.x,
+                            a->e_pred_frames, h1, h2));
+    }
+    FS2_TRY(add_positions(f.x, m->dec_pos, B, T, D, s));
+  }
   for (int i = 0; i < m->n_dec; i++) FS2_TRY(fft_block(s, m, m->dec[i], f, B, T, a->mel_mask_lens, (m->tc_mask & FS2_TC_DECODER) != 0));
   const bool tcp = (m->tc_mask & FS2_TC_POSTNET) != 0;
   FS2_TRY(conv(s, f.x, B, T, D, m->w_mel, tcp ? m->w_mel_tc : nullptr, m->b_mel, m->n_mel, 1, 1, 0, FS2_ACT_NONE, 0.f, a->mel));
@@ -296,7 +325,7 @@ using namespace fs2;
 
 extern "C" {
 
-int fs2_abi_version(void) { return 3; }
+int fs2_abi_version(void) { return 4; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count; }
 size_t fs2_struct_size(int which) {
@@ -358,6 +387,7 @@ int fs2_variance_head(const fs2_variance_head_args* a, fs2_stream_t st) { return
 int fs2_durations(const fs2_durations_args* a, fs2_stream_t st) { return durations(a, S(st)); }
 int fs2_length_regulate(const fs2_length_regulate_args* a, fs2_stream_t st) { return length_regulate(a, S(st)); }
 int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t st) { return conv_post(a, S(st)); }
+int fs2_add_positions(float* x, const float* pos, int B, int T, int D, fs2_stream_t st) { return add_positions(x, pos, B, T, D, S(st)); }
 int fs2_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, fs2_stream_t st) {
   return transpose_bct_to_btc(in, out, B, C, T, S(st));
 }
@@ -373,7 +403,7 @@ size_t fs2_encode_workspace_bytes(const fs2_acoustic_model* m, int B, int L) {
 
 int fs2_acoustic_encode(const fs2_acoustic_model* m, const fs2_encode_args* a, fs2_stream_t st) {
   if (!model_ok(m) || !a || a->B <= 0 || a->L <= 0) return FS2_ERR_ARG;
-  if (!a->texts || !a->src_lens || !a->p_pred || !a->e_pred || !a->logd_pred || !a->mel_lens || !a->cum_dur || !a->x_adapted ||
+  if (!a->texts || !a->src_lens || !a->logd_pred || !a->mel_lens || !a->cum_dur || !a->x_adapted ||
       !a->len_stats || !a->workspace)
     return FS2_ERR_ARG;
   if (!a->d_target && !a->d_rounded) return FS2_ERR_ARG;

@@ -61,6 +61,31 @@ int add_speaker(const fs2_rowbias_args* a, cudaStream_t s) {
   return FS2_OK;
 }
 
+// ------------------------------------------------------------------ x[b,t,:] += pos[t,:]
+__global__ void add_positions_kernel(float* __restrict__ x, const float* __restrict__ pos, long long rows, int T, int D4) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int t = (int)(row % T);
+  float4* o = reinterpret_cast<float4*>(x) + row * D4;
+  const float4* p = reinterpret_cast<const float4*>(pos) + (long long)t * D4;
+  for (int c = lane; c < D4; c += 32) {
+    const float4 a = __ldg(p + c);
+    float4 v = o[c];
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    o[c] = v;
+  }
+}
+
+int add_positions(float* x, const float* pos, int B, int T, int D, cudaStream_t s) {
+  if (!x || !pos || B <= 0 || T <= 0 || D <= 0) return FS2_ERR_ARG;
+  if (D % 4) return FS2_ERR_UNSUPPORTED;
+  const long long rows = (long long)B * T;
+  add_positions_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, pos, rows, T, D / 4);
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
 // ------------------------------------------------------------------ LayerNorm + pad-row zeroing
 // One warp per row; the row lives in registers (C <= 1024), two-pass mean / variance like ATen's CPU kernel.
 __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int T, int C4,

@@ -118,6 +118,8 @@ class FastSpeech2(nn.Module):
         for name in ("pitch_bins", "energy_bins", "pitch_emb", "energy_emb", "w_mel", "b_mel"):
             setattr(m, name, P(name))
         m.tc_mask = self.tc_mask
+        m.pitch_frame_level = int(self.pitch_feature_level == "frame_level")
+        m.energy_frame_level = int(self.energy_feature_level == "frame_level")
         m.w_mel_tc = P("w_mel_tc") if "w_mel_tc" in pk else 0
         m.n_postnet = n_post
         for i in range(n_post):
@@ -156,8 +158,8 @@ class FastSpeech2(nn.Module):
                 p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0, d_control=1.0):
         if self.training:
             raise NotImplementedError("B200-native FastSpeech2 is inference-only: call .eval() (utils/model.py:32)")
-        if self.pitch_feature_level != "phoneme_level" or self.energy_feature_level != "phoneme_level":
-            raise NotImplementedError("frame_level pitch/energy (config/LJSpeech_paper) is not on the sm_100a path yet")
+        p_frame = self.pitch_feature_level == "frame_level"
+        e_frame = self.energy_feature_level == "frame_level"
         lib = L.lib()
         m, _keep, dev = self._packed or self._pack()
         B, Lmax = int(texts.shape[0]), int(max_src_len)
@@ -190,8 +192,8 @@ class FastSpeech2(nn.Module):
         ws = self._workspace(ws_bytes, dev)
         ea = L.EncodeArgs(B=B, L=Lmax, texts=texts.data_ptr(), speakers=L.ptr(speakers_d), src_lens=src_lens32.data_ptr(),
                           p_control=float(p_control), e_control=float(e_control), d_control=float(d_control),
-                          p_target=L.ptr(p_t), e_target=L.ptr(e_t), d_target=L.ptr(d_t),
-                          p_pred=p_pred.data_ptr(), e_pred=e_pred.data_ptr(), logd_pred=logd.data_ptr(),
+                          p_target=0 if p_frame else L.ptr(p_t), e_target=0 if e_frame else L.ptr(e_t), d_target=L.ptr(d_t),
+                          p_pred=0 if p_frame else p_pred.data_ptr(), e_pred=0 if e_frame else e_pred.data_ptr(), logd_pred=logd.data_ptr(),
                           d_rounded=d_rounded.data_ptr(), mel_lens=mel_lens_out.data_ptr(), mel_lens32=mel_lens32.data_ptr(),
                           cum_dur=cum.data_ptr(), x_adapted=x_adapted.data_ptr(), len_stats=stats_dev.data_ptr(),
                           len_stats_host=self._stats_host.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
@@ -213,10 +215,21 @@ class FastSpeech2(nn.Module):
         m.dec_pos, m.dec_pos_rows = self._position(1, T, m.d_model, dev)
         mel = torch.empty(B, T, m.n_mel, **f32)
         post = torch.empty(B, T, m.n_mel, **f32)
+        if p_frame:                                    # frame-level predictions have the mel time axis (model/modules.py:139-148)
+            p_pred = torch.empty(B, T, **f32)
+            if p_t is not None and tuple(p_t.shape) != (B, T):
+                raise ValueError("frame-level p_targets must be [B, max_mel_len]")
+        if e_frame:
+            e_pred = torch.empty(B, T, **f32)
+            if e_t is not None and tuple(e_t.shape) != (B, T):
+                raise ValueError("frame-level e_targets must be [B, max_mel_len]")
         ws_bytes = lib.fs2_decode_workspace_bytes(C.byref(m), B, T)
         ws = self._workspace(ws_bytes, dev)
         da = L.DecodeArgs(B=B, L=Lmax, T=T, x_adapted=x_adapted.data_ptr(), cum_dur=cum.data_ptr(),
-                          mel_mask_lens=mask_lens32.data_ptr(), mel=mel.data_ptr(), postnet_mel=post.data_ptr(),
+                          mel_mask_lens=mask_lens32.data_ptr(), p_control=float(p_control),
+                          p_target_frames=L.ptr(p_t) if p_frame else 0, e_target_frames=L.ptr(e_t) if e_frame else 0,
+                          p_pred_frames=p_pred.data_ptr() if p_frame else 0, e_pred_frames=e_pred.data_ptr() if e_frame else 0,
+                          mel=mel.data_ptr(), postnet_mel=post.data_ptr(),
                           workspace=ws.data_ptr(), workspace_bytes=ws.numel())
         L.check(lib.fs2_acoustic_decode(C.byref(m), C.byref(da), stream), "fs2_acoustic_decode")
 

@@ -149,6 +149,9 @@ typedef struct fs2_conv_post_args {
 } fs2_conv_post_args;
 int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t stream);
 
+/* x[b,t,:] += pos[t,:]   (decoder position add when the length regulator could not fuse it: frame-level variance configs) */
+int fs2_add_positions(float* x, const float* pos, int B, int T, int D, fs2_stream_t stream);
+
 /* out[b,t,c] = in[b,c,t]  (mel [B,80,T] -> channels-last) */
 int fs2_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, fs2_stream_t stream);
 
@@ -175,6 +178,7 @@ typedef struct fs2_acoustic_model {
   int vp_filter, vp_kernel, n_bins, n_vocab, n_speakers;
   int enc_pos_rows, dec_pos_rows;            /* rows available in the position tables */
   int tc_mask;                               /* FS2_TC_* bits; parts not selected run the fp32 CUDA-core kernels */
+  int pitch_frame_level, energy_frame_level; /* 0 = phoneme-level predictor (before the length regulator), 1 = frame-level (after it): model/modules.py:117-126 vs :139-148 */
   const float *word_emb, *enc_pos, *dec_pos, *spk_emb;
   fs2_fft_block_weights enc[FS2_MAX_LAYERS], dec[FS2_MAX_LAYERS];
   fs2_predictor_weights dur, pitch, energy;
@@ -211,6 +215,9 @@ typedef struct fs2_decode_args {
   int B, L, T;
   const float* x_adapted; const int32_t* cum_dur;
   const int32_t* mel_mask_lens;  /* [B]: rows t >= len are padding for the decoder masks */
+  float p_control;               /* used by frame-level pitch AND energy (the reference passes p_control to both, modules.py:146) */
+  const float *p_target_frames, *e_target_frames; /* [B][T] or NULL (frame-level configs, teacher forcing) */
+  float *p_pred_frames, *e_pred_frames;           /* [B][T] outputs, required for the predictors configured frame-level */
   float* mel; float* postnet_mel; /* [B][T][n_mel] */
   void* workspace; size_t workspace_bytes;
 } fs2_decode_args;

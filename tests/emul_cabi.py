@@ -120,7 +120,7 @@ def length_regulate(x, cum, pos, T):
 
 
 def acoustic_forward(pk, cfg, speakers, texts, src_lens, p_control=1.0, d_control=1.0, p_target=None, e_target=None,
-                     d_target=None, mel_lens=None, max_mel_len=None):
+                     d_target=None, mel_lens=None, max_mel_len=None, pitch_frame=False, energy_frame=False):
     """Mirror of encode_impl + decode_impl in model.cu.  cfg: dict(n_head,k1,k2,n_enc,n_dec,vp_kernel,n_postnet,post_k)."""
     B, L = texts.shape
     lens = src_lens.to(torch.int32)
@@ -131,12 +131,23 @@ def acoustic_forward(pk, cfg, speakers, texts, src_lens, p_control=1.0, d_contro
         x = x + pk["spk_emb"][speakers][:, None, :]
     k = cfg["vp_kernel"]
     logd, _ = predictor(pk, "dur", x, lens, k)
-    p_pred, x = predictor(pk, "pitch", x, lens, k, p_control, p_target, pk["pitch_bins"], pk["pitch_emb"], x)
-    e_pred, x = predictor(pk, "energy", x, lens, k, p_control, e_target, pk["energy_bins"], pk["energy_emb"], x)
+    p_pred = e_pred = None
+    if not pitch_frame:
+        p_pred, x = predictor(pk, "pitch", x, lens, k, p_control, p_target, pk["pitch_bins"], pk["pitch_emb"], x)
+    if not energy_frame:
+        e_pred, x = predictor(pk, "energy", x, lens, k, p_control, e_target, pk["energy_bins"], pk["energy_emb"], x)
     d_rounded, cum, mel_len = durations(d_target if d_target is not None else logd, d_target is not None, d_control)
     T = int(max_mel_len) if max_mel_len is not None else int(mel_len.max())
     mask_lens = (mel_lens if mel_lens is not None else mel_len).to(torch.int32)
-    y = length_regulate(x, cum, pk["dec_pos"], T)
+    if pitch_frame or energy_frame:                  # decode_impl: LR without positions, frame-level heads, then fs2_add_positions
+        y = length_regulate(x, cum, torch.zeros_like(pk["dec_pos"]), T)
+        if pitch_frame:
+            p_pred, y = predictor(pk, "pitch", y, mask_lens, k, p_control, p_target, pk["pitch_bins"], pk["pitch_emb"], y)
+        if energy_frame:
+            e_pred, y = predictor(pk, "energy", y, mask_lens, k, p_control, e_target, pk["energy_bins"], pk["energy_emb"], y)
+        y = y + pk["dec_pos"][:T]
+    else:
+        y = length_regulate(x, cum, pk["dec_pos"], T)
     for i in range(cfg["n_dec"]):
         y = fft_block(pk, f"dec.{i}.", y, mask_lens, cfg["n_head"], cfg["k1"], cfg["k2"])
     mel = conv1d(y, pk["w_mel"][None], pk["b_mel"])

@@ -42,6 +42,23 @@ def test_acoustic_teacher_forced_libri(libri_configs):
         assert (got - want).abs().max() < 2e-5
 
 
+def test_acoustic_frame_level_variances(scratch):
+    """config/LJSpeech_paper style: pitch / energy predicted per mel frame after the length regulator (modules.py:139-148)."""
+    import copy
+    pc, mc = configs.make_configs("LJSpeech", scratch)
+    pc = copy.deepcopy(pc)
+    pc["preprocessing"]["pitch"]["feature"] = "frame_level"
+    pc["preprocessing"]["energy"]["feature"] = "frame_level"
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=8)
+    spk, texts, lens, L = synth.make_batch(2, 18, seed=9, min_len=11)
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, L, p_control=0.9, pitch_level="frame_level", energy_level="frame_level")
+    mel, post, p, e, logd, d, mel_len = E.acoustic_forward(_pk(sd, False), CFG, spk, texts, lens, p_control=0.9, pitch_frame=True,
+                                                          energy_frame=True)
+    assert torch.equal(mel_len, ref[9]) and p.shape == ref[2].shape == mel.shape[:2]
+    for got, want in ((mel, ref[0]), (post, ref[1]), (p, ref[2]), (e, ref[3]), (logd, ref[4])):
+        assert (got - want).abs().max() < 2e-5
+
+
 def test_vocoder_decomposition():
     h = configs.HIFIGAN_CONFIG
     sd = synth.hifigan_state_dict(h, seed=2)

@@ -70,6 +70,24 @@ def test_fastspeech2_ragged_multispeaker_long(libri_configs, parity_log):
     assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
 
 
+def test_fastspeech2_frame_level_variances(scratch, parity_log):
+    """pitch / energy feature = frame_level (config/LJSpeech_paper): predictors run on the expanded sequence."""
+    import copy
+    pc, mc = configs.make_configs("LJSpeech", scratch)
+    pc = copy.deepcopy(pc)
+    pc["preprocessing"]["pitch"]["feature"] = "frame_level"
+    pc["preprocessing"]["energy"]["feature"] = "frame_level"
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=15)
+    m = FastSpeech2(pc, mc); m.load_state_dict(sd); m = m.to(DEV).eval()
+    spk, texts, lens, Lm = synth.make_batch(3, 40, seed=16, min_len=21)
+    ref = O.fastspeech2_forward(sd, spk, texts, lens, Lm, p_control=1.1, pitch_level="frame_level", energy_level="frame_level")
+    out = m(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm, p_control=1.1)
+    assert torch.equal(out[9].cpu(), ref[9]) and out[2].shape == ref[2].shape
+    e = _cmp(out, ref)
+    parity_log("fs2_frame_level_B3_L40", **e)
+    assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL and max(e["pitch"], e["energy"]) < 1e-4, e
+
+
 def test_fastspeech2_teacher_forced(lj_configs, parity_log):
     m, sd = _model(lj_configs, seed=5)
     spk, texts, lens, Lm = synth.make_batch(4, 48, seed=6, min_len=15)

@@ -105,3 +105,26 @@ def test_oracle_vs_live_reference(scratch):
     with torch.no_grad():
         w = gen(mel)
     assert (O.hifigan_forward(hsd, mel) - w).abs().max() < 1e-5
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_oracle_frame_level_vs_live_reference(scratch):
+    """frame_level pitch / energy (config/LJSpeech_paper, model/modules.py:139-148): oracle vs the unmodified reference."""
+    import copy
+    FastSpeech2, _ = ref_import.load()
+    pc, mc = configs.make_configs("LJSpeech", scratch)
+    pc = copy.deepcopy(pc)
+    pc["preprocessing"]["pitch"]["feature"] = "frame_level"
+    pc["preprocessing"]["energy"]["feature"] = "frame_level"
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=41)
+    ref = FastSpeech2(pc, mc)
+    ref.load_state_dict(sd)
+    ref.eval()
+    spk, texts, lens, L = synth.make_batch(2, 22, seed=42, min_len=13)
+    with torch.no_grad():
+        want = ref(spk, texts, lens, L, p_control=1.2)
+    got = O.fastspeech2_forward(sd, spk, texts, lens, L, p_control=1.2, pitch_level="frame_level", energy_level="frame_level")
+    assert torch.equal(got[9], want[9]) and got[2].shape == want[2].shape == want[0].shape[:2]
+    for i in range(5):
+        assert (got[i] - want[i]).abs().max() < 5e-6
