@@ -31,16 +31,26 @@ def _stub():
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
 
 
+_loaded = None
+
+
 def load():
     """Returns (FastSpeech2 class, hifigan module) from the reference tree."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
     if not available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     _stub()
     for m in ("model", "hifigan", "transformer", "utils", "text"):
-        if m in sys.modules and REFERENCE_ROOT not in (getattr(sys.modules[m], "__file__", "") or ""):
-            raise RuntimeError(f"module {m!r} already imported from elsewhere; run the reference in its own process")
+        if m in sys.modules:
+            mod = sys.modules[m]
+            where = [getattr(mod, "__file__", None) or ""] + list(getattr(mod, "__path__", []) or [])
+            if not any(REFERENCE_ROOT in w for w in where):
+                raise RuntimeError(f"module {m!r} already imported from elsewhere; run the reference in its own process")
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import hifigan                                   # noqa: E402
     from model import FastSpeech2                    # noqa: E402
-    return FastSpeech2, hifigan
+    _loaded = (FastSpeech2, hifigan)
+    return _loaded
