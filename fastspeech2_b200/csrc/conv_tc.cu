@@ -640,7 +640,7 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   if (mt > tiles128) mt = tiles128 >= 2 ? 2 : 1;
   if (mt == 2 && mt * 128 + halo > TC_LD * TC_TTHREADS / TC_CHUNKS) mt = 1;   // rows one register-ring slot can hold
   // small problems (decoder projections, attention PV): prefer more, smaller work items when MT = 2 would leave SMs idle
-  if (mt == 2 && (long long)(a->N / p.NB) * a->B * ((a->T + 255) / 256) < g_num_sms) mt = 1;
+  if (mt == 2 && 2LL * (a->N / p.NB) * a->B * ((a->T + 255) / 256) <= g_num_sms) mt = 1;   // measured: helps at <= 1/2 wave, hurts K-heavy layers at ~1 wave
   int R = mt * 128 + halo;
   R += (12 - (R & 7)) & 7;                             // R % 8 == 4: conflict-free transform stores (2 chunks per row)
   p.MT = mt; p.R = R;
