@@ -3,11 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "fs2b200.h"
 
 namespace fs2 {
 
-extern unsigned long long g_launch_count;  // host-side counter, bumped once per kernel launch
+extern std::atomic<unsigned long long> g_launch_count;  // host-side counter, bumped once per kernel launch (any thread)
 
 inline int cuda_status() {
   cudaError_t e = cudaGetLastError();

@@ -7,7 +7,7 @@
 
 namespace fs2 {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // ------------------------------------------------------------------ per-launch profiling (off unless armed)
 bool g_prof_on = false;
@@ -327,7 +327,7 @@ extern "C" {
 
 int fs2_abi_version(void) { return 4; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
-int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count; }
+int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count.load(); }
 size_t fs2_struct_size(int which) {
   switch (which) {
     case 0: return sizeof(fs2_conv1d_args);
