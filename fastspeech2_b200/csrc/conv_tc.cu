@@ -70,7 +70,7 @@ struct TcP {
   int acc_stride;                  // TMEM columns between accumulators
   int tmem_cols;                   // power of two >= 2*MT*TG*acc_stride
   long long* trace;                // debug: [CTA][16 items][8] globaltimer stamps, or NULL
-  unsigned variant;                // debug knobs: 1 = transform skips global loads, 2 = transform skips the split math, 4 = epilogue skips global stores, 8 = late residual loads, 16/32/64 = wait policy
+  unsigned variant;                // debug knobs: 1 = transform skips global loads, 2 = transform skips the split math, 4 = epilogue skips global stores
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -95,37 +95,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
-}
-// Waits of roles that run ahead of their consumer (producer, transform, epilogue) do not need the lowest wake-up latency;
-// their polls share the shared-memory pipe with the tensor core's operand reads.  mode bit 0: bounded hardware suspend
-// (try_wait with a suspend-time hint), bit 1: nanosleep back-off between polls.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t mode) {
-  if (mode & 1u) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITH_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONEH_%=;\n\t"
-        "bra WAITH_%=;\n\t"
-        "DONEH_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(100000u)
-        : "memory");
-  } else if (mode & 2u) {
-    uint32_t done = 0;
-    while (true) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(smem_u32(bar)), "r"(parity)
-          : "memory");
-      if (done) break;
-      __nanosleep(64);
-    }
-  } else {
-    mbar_wait(bar, parity);
-  }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -164,27 +133,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// issue / wait halves of tc_ld32 for the software-pipelined epilogue (the wait names the registers so no use can move above it)
-__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld32_wait(uint32_t (&v)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
-                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
-                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
-                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-               :
-               : "memory");
 }
 
 // UMMA shared-memory descriptor, no-swizzle K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
@@ -243,13 +191,9 @@ __device__ __forceinline__ float tc_act(float v, float slope) {
 
 // One 32-row x W-column block of one accumulator: TMEM -> regs -> smem transpose -> coalesced global I/O.
 // W = 32: 8 lanes per row, 4 rows per pass, 8 passes.  W = 16: 4 lanes per row, 8 rows per pass, 4 passes.
-// PIPE: the caller already issued the tcgen05.ld of this block into `v` (tc_ld32_issue); after the transpose tile is written the
-// load of the next block (`next_taddr`, 0 = none) is issued into the same registers, so its TMEM latency overlaps the global
-// I/O of this block.
-template <int ACT, int W, bool FULL, bool PIPE = false>
+template <int ACT, int W, bool FULL>
 __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, float* stage, int lane, float* yptr, const float* rptr,
-                                                  const float* bias, int rows_live, int rows_valid, float inv_ws, uint32_t (&v)[32],
-                                                  uint32_t next_taddr = 0) {
+                                                  const float* bias, int rows_live, int rows_valid, float inv_ws) {
   constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI, HALF = ITERS / 2;
   const int rr = lane / LPR;
   const long long ystep = (long long)RPI * p.yrs, rstep = (long long)RPI * p.rrs;
@@ -268,9 +212,8 @@ __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, 
       if (FULL || k * RPI + rr < rows_valid) r0[k] = *reinterpret_cast<const float4*>(rptr + k * rstep);
   }
   {
-    if (PIPE) tc_ld32_wait(v);
-    else if (W == 32) tc_ld32(taddr, v);
-    else tc_ld16(taddr, v);
+    uint32_t v[32];
+    if (W == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
     for (int g = 1; g < p.TG; g++) {                   // split-term accumulators are summed here, in fp32 round-to-nearest
       uint32_t u[32];
       if (W == 32) tc_ld32(taddr + g * p.acc_stride, u); else tc_ld16(taddr + g * p.acc_stride, u);
@@ -283,7 +226,6 @@ __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, 
           make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]), __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
   }
   __syncwarp();
-  if (PIPE && next_taddr) tc_ld32_issue(next_taddr, v);
   const float slope = p.out_slope, alpha = p.alpha;
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias));
@@ -334,46 +276,9 @@ __device__ __forceinline__ void tc_epilogue_block(const TcP& p, uint32_t taddr, 
   __syncwarp();   // the staging tile is rewritten by the next block
 }
 
-// Pipelined walk over the 32x32 blocks of one work item (NB % 32 == 0): block i+1's TMEM load is in flight while block i is
-// transposed, combined with bias / residual / accumulate and written out.
-template <int ACT>
-__device__ __forceinline__ void tc_epilogue_item_pipe(const TcP& p, uint32_t tmem_acc, float* stage, int q, int lane, const Item& it, float inv_ws) {
-  const int NB = p.NB, n0 = it.nblk * NB, nc = NB >> 5;
-  const int len_b = p.row_lens ? min(p.row_lens[it.b], p.T) : p.T;
-  const int rows_left = p.T - it.t0 - q * 32;           // tiles with rows_valid > 0 form a prefix of the item's MT tiles
-  const int n_mt = rows_left <= 0 ? 0 : min(p.MT, (rows_left + 127) >> 7);
-  const int nblocks = n_mt * nc;
-  if (nblocks == 0) return;
-  const uint32_t tq = tmem_acc + ((uint32_t)(q * 32) << 16);
-  const uint32_t tile_cols = (uint32_t)(p.TG * p.acc_stride);
-  const int rr = lane >> 3, cc = (lane & 7) * 4;
-  uint32_t v[32];
-  tc_ld32_issue(tq, v);
-  int mt = 0, cb = 0;
-  for (int i = 0; i < nblocks; i++) {
-    const int row0 = it.t0 + mt * 128 + q * 32, c = cb * 32;
-    const int rows_valid = min(32, p.T - row0), rows_live = min(32, len_b - row0);
-    const bool full = rows_valid == 32 && rows_live == 32;
-    float* yptr = p.y + (long long)it.b * p.ybs + (long long)(row0 + rr) * p.yrs + n0 + c + cc;
-    const float* rptr = p.res ? p.res + (long long)it.b * p.rbs + (long long)(row0 + rr) * p.rrs + n0 + c + cc : nullptr;
-    const float* bias = p.bias ? p.bias + n0 + c + cc : nullptr;
-    const uint32_t taddr = tq + (uint32_t)mt * tile_cols + (uint32_t)c;
-    int nmt = mt, ncb = cb + 1;
-    if (ncb == nc) { ncb = 0; nmt++; }
-    const uint32_t next = i + 1 < nblocks ? tq + (uint32_t)nmt * tile_cols + (uint32_t)(ncb * 32) : 0u;
-    if (full) tc_epilogue_block<ACT, 32, true, true>(p, taddr, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws, v, next);
-    else tc_epilogue_block<ACT, 32, false, true>(p, taddr, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws, v, next);
-    mt = nmt; cb = ncb;
-  }
-}
-
 template <int ACT>
 __device__ __forceinline__ void tc_epilogue_item(const TcP& p, uint32_t tmem_acc, float* stage, int q, int lane, const Item& it, float inv_ws) {
   const int NB = p.NB, n0 = it.nblk * NB;
-  if ((p.variant & 128u) && (NB & 31) == 0) {
-    tc_epilogue_item_pipe<ACT>(p, tmem_acc, stage, q, lane, it, inv_ws);
-    return;
-  }
   const int len_b = p.row_lens ? min(p.row_lens[it.b], p.T) : p.T;
   for (int mt = 0; mt < p.MT; mt++) {
     const int row0 = it.t0 + mt * 128 + q * 32;
@@ -389,12 +294,11 @@ __device__ __forceinline__ void tc_epilogue_item(const TcP& p, uint32_t tmem_acc
       float* yptr = p.y + (long long)it.b * p.ybs + (long long)(row0 + rr) * p.yrs + n0 + c + cc;
       const float* rptr = p.res ? p.res + (long long)it.b * p.rbs + (long long)(row0 + rr) * p.rrs + n0 + c + cc : nullptr;
       const float* bias = p.bias ? p.bias + n0 + c + cc : nullptr;
-      uint32_t v[32];
       if (w == 32) {
-        if (full) tc_epilogue_block<ACT, 32, true>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws, v);
-        else tc_epilogue_block<ACT, 32, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws, v);
+        if (full) tc_epilogue_block<ACT, 32, true>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws);
+        else tc_epilogue_block<ACT, 32, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws);
       } else {
-        tc_epilogue_block<ACT, 16, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws, v);
+        tc_epilogue_block<ACT, 16, false>(p, tbase + c, stage, lane, yptr, rptr, bias, rows_live, rows_valid, inv_ws);
       }
     }
   }
@@ -420,8 +324,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
 
   const int KBLOCKS = p.Cin / TC_KB;
-  const uint32_t wmode = (p.variant >> 4) & 3u;                    // wait policy of the run-ahead roles (variant bits 16, 32)
-  const uint32_t cmode = (p.variant & 64u) ? wmode : 0u;           // variant bit 64: same policy for the MMA issuer's waits
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < TC_SA_MAX; i++) { mbar_init(&fullA[i], TC_TW); mbar_init(&emptyA[i], 1); }
@@ -454,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
           for (int tap = 0; tap < p.taps; tap += p.TPS) {
             const int n = min(p.TPS, p.taps - tap);
             const uint32_t bytes = (uint32_t)n * stage_bytes;
-            mbar_wait_relaxed(&emptyB[rb.idx], rb.phase ^ 1, wmode);
+            mbar_wait(&emptyB[rb.idx], rb.phase ^ 1);
             mbar_expect_tx(&fullB[rb.idx], bytes);
             bulk_g2s(b_base + (size_t)rb.idx * p.TPS * stage_bytes, src, bytes, &fullB[rb.idx]);
             src += bytes;
@@ -482,13 +384,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     uint32_t itT = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
       const uint32_t buf = rt.idx;
-      mbar_wait_relaxed(&accEmpty[buf], rt.phase ^ 1, cmode);           // epilogue has drained this accumulator set
+      mbar_wait(&accEmpty[buf], rt.phase ^ 1);                    // epilogue has drained this accumulator set
       tc_fence_after();
       const uint32_t d0 = tmem + buf * acc_set;
       if (leader) TC_STAMP((int)itT, 2);
       for (int kb = 0; kb < KBLOCKS; kb++, ra.advance(SA)) {
         const uint32_t sa = ra.idx;
-        mbar_wait_relaxed(&fullA[sa], ra.phase, cmode);
+        mbar_wait(&fullA[sa], ra.phase);
         tc_fence_after();
         const uint64_t a_hi = a_const | (uint64_t)(smem_u32(a_base + (size_t)sa * 2 * a_plane) >> 4);
         const uint64_t a_lo = a_hi + (a_plane >> 4);
@@ -496,7 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
         for (int tap = 0; tap < p.taps; tap += p.TPS, rb.advance(SB)) {
           const uint32_t sb = rb.idx;
           const int n = min(p.TPS, p.taps - tap);
-          mbar_wait_relaxed(&fullB[sb], rb.phase, cmode);
+          mbar_wait(&fullB[sb], rb.phase);
           tc_fence_after();
           if (leader) {
             uint64_t b_hi = b_const | (uint64_t)(smem_u32(b_base + (size_t)sb * p.TPS * 2 * b_plane) >> 4);
@@ -620,7 +522,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
         const int seq = base + d;
         if (seq < total) {
           if (wt == 0 && s_kb == 0) TC_STAMP(s_il, 0);
-          mbar_wait_relaxed(&emptyA[ra.idx], ra.phase ^ 1, wmode);
+          mbar_wait(&emptyA[ra.idx], ra.phase ^ 1);
           convert_store(v[d], ra.idx);
           fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core (async proxy)
           __syncwarp();
@@ -642,7 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
       const uint32_t buf = rt.idx;
       const Item it = decode_item(p, item);
-      mbar_wait_relaxed(&accFull[buf], rt.phase, wmode);
+      mbar_wait(&accFull[buf], rt.phase);
       tc_fence_after();
       const uint32_t acc = tmem + buf * acc_set;
       if (warp == 2 + TC_TW && lane == 0) TC_STAMP((int)itT, 4);
