@@ -89,12 +89,17 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   const size_t a_stage = (size_t)2 * TC_CHUNKS * R * 16, b_stage = (size_t)tps * tap_bytes;
   const size_t budget = 226 * 1024;
   const int kblocks = a->Cin / TC_KB;
-  int sa = kblocks < 3 ? 2 : 3, sb = tps > 1 ? 4 : TC_SB_MAX;   // ring depths matter little (measured); keep both rings >= 2-3 deep
+  // Slab ring depth, measured per shape class (scripts/tc_tune_sa.py, profiles/r01_tc_tune_sa.txt): the ring spans work items, so
+  // even 2-K-block layers want 3 stages (-10..-14 % on the 32-channel stage against 2); k <= 3 layers like 5 (-4..-6 %); a
+  // 4th MT=4 stage is not worth shrinking the weight ring for.
+  int sa = 3, sb = tps > 1 ? 4 : TC_SB_MAX;
+  if (mt < 4 && a->taps <= 3) sa = 5;
+  else if (mt < 4 && kblocks >= 4) sa = 4;
+  while (fixed + sa * a_stage + sb * b_stage > budget && sa > 3) sa--;
   while (fixed + sa * a_stage + sb * b_stage > budget && sb > 3) sb--;
   while (fixed + sa * a_stage + sb * b_stage > budget && sa > 2) sa--;
   while (fixed + sa * a_stage + sb * b_stage > budget && sb > 2) sb--;
   if (fixed + sa * a_stage + sb * b_stage > budget) return FS2_ERR_UNSUPPORTED;
-  if (sa < 4 && kblocks >= 4 && fixed + (sa + 1) * a_stage + sb * b_stage <= budget) sa++;
   if (g_tc_tune[0] > 0) sa = g_tc_tune[0] > TC_SA_MAX ? TC_SA_MAX : g_tc_tune[0];
   if (g_tc_tune[1] > 0) sb = g_tc_tune[1] > TC_SB_MAX ? TC_SB_MAX : g_tc_tune[1];
   if (fixed + sa * a_stage + sb * b_stage > budget) return FS2_ERR_UNSUPPORTED;
