@@ -292,7 +292,13 @@ def run_ours(args):
         ms = (C.c_double * 4)(); fl = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
         lib.fs2_profile_end(ms, fl, cnt)
         pk = peaks()
-        achieved = fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
+        # Bracketing every launch with two events costs a bubble per launch (the bracketed conv launches alone add up to more than
+        # the whole timed step), so the class's duration inside the TIMED region is taken as its share of the bracketed pass times
+        # the event-timed step; the raw bracketed figure is reported next to it.
+        bracketed = fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
+        share = ms[0] / max(sum(ms), 1e-9)
+        conv_ms = share * ms_total / args.steps
+        achieved = fl[0] / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tp):
@@ -300,8 +306,9 @@ def run_ours(args):
         roof = {"kernel": "conv1d implicit-GEMM (all launches of one step: FFT-block projections / conv-FFN, predictors, PostNet, HiFi-GAN convs)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops_sustained"], "peak_source": pk["source"] + ", bf16 sustained (kernel timed inside a long step)",
-                "traffic": traffic, "launches_per_step": int(cnt[0]), "avg_launch_ms": ms[0] / max(int(cnt[0]), 1),
-                "share_of_step": ms[0] / max(sum(ms), 1e-9),
+                "traffic": traffic, "launches_per_step": int(cnt[0]), "avg_launch_ms": conv_ms / max(int(cnt[0]), 1),
+                "share_of_step": share, "achieved_event_bracketed": bracketed, "avg_launch_ms_event_bracketed": ms[0] / max(int(cnt[0]), 1),
+                "timing": "class share from one untimed step with CUDA events around every launch x the event-timed step",
                 "other_classes_ms": {"attention": ms[1], "layernorm": ms[2], "other": ms[3]},
                 "algorithmic_tflop_per_step": fl[0] / 1e12}
 

@@ -8,7 +8,7 @@
 // fp32): 22 significant bits, the same as a TF32 hi/lo split, but kind::f16 MMAs have K = 16 per instruction -- twice the
 // FLOPs per instruction and per shared-memory byte of kind::tf32.  D += A_lo*B_hi + A_hi*B_hi + A_hi*B_lo, fp32 accumulate in
 // TMEM.  Weights are pre-scaled by a per-layer power of two (kept in a 128-byte header of the tiled buffer) so that their lo
-// parts stay in fp16's normal range; activations are used unscaled (|x| <= 65504 clamp; a lo part below 2^-14 only costs an
+// parts stay in fp16's normal range; activations are used unscaled (|x| > 65504 saturates in the convert; a lo part below 2^-14 only costs an
 // ABSOLUTE error < 3e-8).  Emulated end to end on the CPU (exact accumulation) this split is as accurate as fp32 convolution
 // on both the synthetic and the shipped HiFi-GAN checkpoint; on the GPU the tensor core's round-toward-zero accumulator is
 // what remains (profiles/r01_tc_accumulate_bias.txt), and K = 16 halves the number of accumulation steps.
@@ -18,7 +18,7 @@
 //   warp 0      weight producer: every (tap, 16-channel K-block) weight stage is ONE cp.async.bulk (TMA bulk engine) of a
 //               host-pre-split, host-pre-tiled smem image  [hi|lo][16-byte K-chunk][n][8 halfs].
 //   warps 2-9   activation transform: read the [MT*128 + (taps-1)*dil] x 16-channel slab of a K-block ONCE from global
-//               (float4, a 3-deep register ring of K-blocks in flight: ~60 KB of loads per SM, what HBM latency x bandwidth needs), apply the input activation, split hi/lo and store both in the
+//               (one 256-bit load per row and 8 channels, a 3-deep register ring of K-blocks in flight: ~60 KB of loads per SM), apply the input activation, split hi/lo and store both in the
 //               UMMA no-swizzle K-major layout [16-byte K-chunk][row][8 halfs].  There a core matrix (8 rows x 16 B)
 //               starting at ANY row is 128 contiguous bytes, so each conv tap is just the same slab with the descriptor start
 //               address advanced by tap*dil rows: the slab is loaded and split once per K-block, not once per tap.
