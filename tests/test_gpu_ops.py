@@ -93,6 +93,37 @@ def test_conv1d_tensor_core(case):
     assert err < 6e-5, err
 
 
+def test_conv1d_tensor_core_alignment_contract():
+    """The tcgen05 kernel reads activations with 256-bit loads: a 16-byte-but-not-32-byte aligned x is refused by the explicit
+    backend and silently served by the exact fp32 kernel under FS2_CONV_AUTO (same contract, fp32 accuracy)."""
+    from fastspeech2_b200._lib import Fs2Error
+    B, T, Cin, N = 2, 200, 64, 64
+    buf = rnd(B * T * Cin + 8, seed=11).to(DEV)
+    x = buf[4:4 + B * T * Cin].view(B, T, Cin)
+    assert x.data_ptr() % 32 == 16
+    w = rnd(3, Cin, N, seed=12, scale=0.1)
+    wtc = packing.pack_conv_tc(w).to(DEV)
+    with pytest.raises(Fs2Error):
+        ops.conv1d(x, w.to(DEV), None, pad_left=1, w_tc=wtc, backend=2)
+    got = ops.conv1d(x, w.to(DEV), None, pad_left=1, w_tc=wtc, backend=0)
+    torch.cuda.synchronize()
+    want = E.conv1d(x.cpu().double(), w.double(), None, 1, 1, 0, 0.0, 0, 0.0, None, 1.0, None, None)
+    assert (got.cpu().double() - want).abs().max().item() < 5e-6
+
+
+def test_conv1d_tensor_core_large_activations():
+    """|x| beyond the fp16 range saturates in the hi/lo split instead of turning into inf / NaN (hi = 65504, lo = fp16(x - hi))."""
+    B, T, Cin, N = 1, 128, 16, 16
+    x = rnd(B, T, Cin, seed=13)
+    x[0, 5, 3] = 7.0e4; x[0, 9, 0] = -9.0e4
+    w = rnd(1, Cin, N, seed=14, scale=0.1)
+    got = ops.conv1d(x.to(DEV), w.to(DEV), None, w_tc=packing.pack_conv_tc(w).to(DEV), backend=2)
+    torch.cuda.synchronize()
+    want = E.conv1d(x.double(), w.double(), None, 1, 0, 0, 0.0, 0, 0.0, None, 1.0, None, None)
+    assert torch.isfinite(got).all()
+    assert (got.cpu().double() - want).abs().max().item() < 2e-3 * want.abs().max().item()
+
+
 def test_conv1d_strided_output_conv_transpose():
     for u, cin, cout, T in ((8, 64, 32, 37), (2, 64, 32, 130)):
         w = rnd(cin, cout, 2 * u, seed=7, scale=0.1)
