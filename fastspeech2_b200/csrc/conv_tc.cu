@@ -34,6 +34,10 @@ bool conv_tc_supported(const fs2_conv1d_args* a) {
 }
 
 static int g_num_sms = 0;
+int g_tc_pdl = 0;                  // programmatic dependent launch: 0 = off (default), 1 = short launches only, 2 = every launch.
+                                   // Measured with the three modes interleaved step by step (scripts/pdl_ab.py,
+                                   // profiles/r01_pdl_ab.txt): no gain on either forward (39.5 / 40.8 / 42.2 ms per step), so it
+                                   // stays off; debug switch fs2_debug_set_tc_pdl
 int g_tc_tune[4] = {0, 0, 0, 0};   // debug overrides: SA, SB, TPS, grid (0 = heuristic); set through fs2_debug_set_tc_tuning
 
 // `wt` must be the tiled layout produced by fastspeech2_b200.packing.pack_conv_tc (see fs2b200.h)
@@ -110,6 +114,7 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   const long long n_items = (long long)(a->N / p.NB) * a->B * p.tiles_per_batch;
   if (n_items > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   p.n_items = (int)n_items;
+  p.pdl = g_tc_pdl == 2 || (g_tc_pdl == 1 && n_items <= 4LL * g_num_sms);
   int grid = n_items < g_num_sms ? (int)n_items : g_num_sms;
   if (g_tc_tune[3] > 0 && g_tc_tune[3] < grid) grid = g_tc_tune[3];
   prof_before(s);

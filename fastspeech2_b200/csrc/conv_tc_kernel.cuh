@@ -73,6 +73,7 @@ struct TcP {
   int tmem_cols;                   // power of two >= 2*MT*TG*acc_stride
   long long* trace;                // debug: [CTA][16 items][8] globaltimer stamps, or NULL
   unsigned variant;                // reserved for A/B experiments (unused by the shipped kernel)
+  int pdl;                         // launched with programmatic stream serialisation: wait for the previous grid before touching its data
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -103,6 +104,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Programmatic dependent launch: the grid may start while its predecessor in the stream is still draining; everything that
+// reads or writes memory the predecessor touches comes after grid_dep_wait() (returns once the predecessor has completed and
+// flushed).  grid_dep_launch() lets the successor's CTAs be scheduled onto SMs as this grid's CTAs exit.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -396,6 +402,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t acc_set = (uint32_t)(MT * TG * p.acc_stride);      // columns per accumulator set
+  if (p.pdl) {
+    grid_dep_launch();
+    // Static weights were written before the stream reached this layer, so the producer warp starts prefetching weight stages
+    // while the predecessor drains; per-utterance "weights" (attention K / V tiles) come from the previous kernel.  The MMA
+    // warp touches no global memory.  Everything else (activation loads, residual / accumulate loads, stores) waits.
+    if (warp >= 2 || (warp == 0 && p.wt_bstride != 0)) grid_dep_wait();
+  }
 
   if (warp == 0) {
     // ===================== weight-stage producer (TMA bulk copies) =====================
@@ -611,6 +624,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols));
   }
+}
+
+inline void conv_tc_launch(void (*kern)(const TcP), const TcP& p, unsigned grid, size_t smem, cudaStream_t s) {
+  if (!p.pdl) {
+    kern<<<grid, TC_THREADS, smem, s>>>(p);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 // Each MT instantiation lives in its own translation unit (conv_tc_mt{1,2,4}.cu) so that the library builds in parallel.

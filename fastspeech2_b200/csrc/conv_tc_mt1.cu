@@ -12,9 +12,10 @@ cudaError_t conv_tc_prepare_mt1(int smem_bytes) {
 }
 
 void conv_tc_launch_mt1(const TcP& p, unsigned grid, size_t smem, cudaStream_t s) {
-  if (p.TG == 3) conv_tc_kernel<1, 3><<<grid, TC_THREADS, smem, s>>>(p);
-  else if (p.TG == 2) conv_tc_kernel<1, 2><<<grid, TC_THREADS, smem, s>>>(p);
-  else conv_tc_kernel<1, 1><<<grid, TC_THREADS, smem, s>>>(p);
+  void (*kern)(const TcP) = conv_tc_kernel<1, 1>;
+  if (p.TG == 2) kern = conv_tc_kernel<1, 2>;
+  if (p.TG == 3) kern = conv_tc_kernel<1, 3>;
+  conv_tc_launch(kern, p, grid, smem, s);
 }
 
 }  // namespace fs2

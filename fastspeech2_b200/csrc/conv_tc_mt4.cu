@@ -11,8 +11,9 @@ cudaError_t conv_tc_prepare_mt4(int smem_bytes) {
 }
 
 void conv_tc_launch_mt4(const TcP& p, unsigned grid, size_t smem, cudaStream_t s) {
-  if (p.TG == 2) conv_tc_kernel<4, 2><<<grid, TC_THREADS, smem, s>>>(p);
-  else conv_tc_kernel<4, 1><<<grid, TC_THREADS, smem, s>>>(p);
+  void (*kern)(const TcP) = conv_tc_kernel<4, 1>;
+  if (p.TG == 2) kern = conv_tc_kernel<4, 2>;
+  conv_tc_launch(kern, p, grid, smem, s);
 }
 
 }  // namespace fs2

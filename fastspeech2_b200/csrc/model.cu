@@ -37,6 +37,7 @@ bool conv_tc_supported(const fs2_conv1d_args* a);
 int conv_tc_nb(int N);
 extern long long* g_tc_trace;
 extern int g_tc_tune[4];
+extern int g_tc_pdl;
 
 // backend dispatch of the fs2_conv1d contract
 static int conv1d_dispatch(const fs2_conv1d_args* a, cudaStream_t s) {
@@ -349,6 +350,7 @@ size_t fs2_struct_size(int which) {
 }
 /* debug only (not in the public header): per-CTA phase timestamps of the next tcgen05 conv launches */
 void fs2_debug_set_tc_trace(long long* buf) { g_tc_trace = buf; }
+void fs2_debug_set_tc_pdl(int on) { g_tc_pdl = on; }
 void fs2_debug_set_tc_tuning(int sa, int sb, int tps, int grid) { g_tc_tune[0] = sa; g_tc_tune[1] = sb; g_tc_tune[2] = tps; g_tc_tune[3] = grid; }
 int fs2_profile_begin(void) {
   g_prof.clear();
