@@ -80,8 +80,9 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   int R = mt * 128 + halo;
   R += (12 - (R & 7)) & 7;                             // R % 8 == 4: conflict-free transform stores (2 chunks per row)
   p.MT = mt; p.R = R;
-  p.TG = p.acc_stride <= 32 ? 3 : (p.acc_stride <= 64 ? 2 : 1);   // spread split terms while two sets still fit in 512 columns
-  if (mt == 4) p.TG = p.acc_stride <= 32 ? 2 : 1;
+  // narrow layers: hi*hi and the two cross terms accumulate in separate TMEM tiles (summed in fp32 round-to-nearest by the
+  // epilogue) while two accumulator sets still fit in 512 columns
+  p.TG = (mt == 4 ? p.acc_stride <= 32 : p.acc_stride <= 64) ? 2 : 1;
   const size_t fixed = 4 * TC_STAGE_FLOATS * sizeof(float) + (2 * TC_SA_MAX + 2 * TC_SB_MAX + 4) * 8 + 16;
   const size_t tap_bytes = (size_t)2 * TC_CHUNKS * p.NB * 16;
   // Taps per weight stage: measured (scripts/tc_tune.py, profiles/r01_tc_tune.txt) -- grouping 4 taps per bulk copy / handshake

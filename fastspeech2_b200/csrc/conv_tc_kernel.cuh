@@ -63,7 +63,7 @@ struct TcP {
   const int* row_lens;
   float* y; long long ybs, yrs;
   int MT;                          // 128-row tiles per work item
-  int TG;                          // accumulators per tile: 1 = all split terms together, 2 = {hi*hi | cross}, 3 = one each
+  int TG;                          // accumulators per tile: 1 = all split terms together, 2 = {hi*hi | the two cross terms}
   int SA, SB;                      // ring depths
   int TPS;                         // conv taps per weight stage (small NB: several taps share one bulk copy / one handshake)
   int R;                           // slab rows held in smem (>= MT*128 + (taps-1)*dil, R % 8 == 4)
@@ -447,8 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const uint32_t idesc = umma_idesc_f16(NB);
     const uint64_t a_const = umma_desc(0, (uint32_t)R * 16, 128), b_const = umma_desc(0, (uint32_t)NB * 16, 128);
     const uint32_t tile_cols = (uint32_t)(TG * p.acc_stride);
-    const uint32_t g_cross = TG >= 2 ? (uint32_t)p.acc_stride : 0u;            // lo*hi (and hi*lo when TG == 2)
-    const uint32_t g_cross2 = TG == 3 ? 2u * (uint32_t)p.acc_stride : g_cross;  // hi*lo
+    const uint32_t g_cross = TG >= 2 ? (uint32_t)p.acc_stride : 0u;            // lo*hi and hi*lo
     Ring ra, rb, rt;
     uint32_t itT = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
@@ -484,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
                 tc_mma_f16(d0 + mt * tile_cols, ah0 + mt * 128, b_hi, idesc, TG >= 2 ? first : 1u);
 #pragma unroll
               for (int mt = 0; mt < MT; mt++)          // A_hi * B_lo
-                tc_mma_f16(d0 + mt * tile_cols + g_cross2, ah0 + mt * 128, b_lo, idesc, TG == 3 ? first : 1u);
+                tc_mma_f16(d0 + mt * tile_cols + g_cross, ah0 + mt * 128, b_lo, idesc, 1u);
             }
             tc_commit(&emptyB[sb]);                    // weight stage free once these MMAs retire
           } else {

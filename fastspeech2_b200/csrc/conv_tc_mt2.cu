@@ -7,14 +7,12 @@ cudaError_t conv_tc_prepare_mt2(int smem_bytes) {
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   return e;
 }
 
 void conv_tc_launch_mt2(const TcP& p, unsigned grid, size_t smem, cudaStream_t s) {
   void (*kern)(const TcP) = conv_tc_kernel<2, 1>;
   if (p.TG == 2) kern = conv_tc_kernel<2, 2>;
-  if (p.TG == 3) kern = conv_tc_kernel<2, 3>;
   conv_tc_launch(kern, p, grid, smem, s);
 }
 
