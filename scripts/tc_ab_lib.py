@@ -1,5 +1,5 @@
 """A/B of two builds of libfs2b200.so inside one process (box-to-box noise is 10-20 %): the in-tree library against
-scratch_ab/libfs2b200_old.so (build of the previous commit).  Same inputs, outputs must match bit for bit.
+a second build passed on the command line (e.g. the previous commit built into scratch_ab/, which is not tracked).  Same inputs, outputs must match bit for bit.
 
 usage: python scripts/tc_ab_lib.py [old.so]
 """
