@@ -32,7 +32,7 @@ class Generator(nn.Module):
         self.num_kernels = len(self._hd["resblock_kernel_sizes"])
         self.num_upsamples = len(self._hd["upsample_rates"])
         self._weight_norm = True
-        self.use_tensor_cores = True     # 3xTF32 tcgen05 kernel for every conv it supports; False = fp32 CUDA-core kernels only
+        self.use_tensor_cores = True     # split-FP16 tcgen05 kernel for every conv it supports; False = fp32 CUDA-core kernels only
         populate(self, hifigan_spec(self._hd, weight_norm=True))
         with torch.no_grad():  # g = ||v|| so that the initial folded weight equals v, as torch's weight_norm does
             for base in self._bases():

@@ -70,6 +70,33 @@ def test_fastspeech2_ragged_multispeaker_long(libri_configs, parity_log):
     assert e["mel"] < MEL_TOL and e["postnet"] < MEL_TOL, e
 
 
+def test_fastspeech2_full_size_tensor_core_vs_exact_path(libri_configs, parity_log):
+    """BASELINE.json configs[3] at FULL size (LibriTTS, B = 64, 64-256 phonemes, Tmax ~ 2000), where the CPU oracle would take
+    minutes: the tcgen05 decoder / PostNet must agree with the independently written exact-fp32 kernels (which the tests above
+    pin to the oracle) on identical decisions, and padded rows must follow the reference's padding semantics."""
+    pc, mc = libri_configs
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=21)
+    fast, exact = FastSpeech2(pc, mc), FastSpeech2(pc, mc)
+    fast.load_state_dict(sd); exact.load_state_dict(sd)
+    exact.tc_mask = 0
+    fast, exact = fast.to(DEV).eval(), exact.to(DEV).eval()
+    spk, texts, lens, Lm = synth.make_batch(64, 256, seed=22, n_speakers=904, min_len=64)
+    a = fast(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm)
+    b = exact(spk.to(DEV), texts.to(DEV), lens.to(DEV), Lm)
+    torch.cuda.synchronize()
+    assert torch.equal(a[5], b[5]) and torch.equal(a[9], b[9]) and torch.equal(a[7], b[7])
+    assert int(a[9].max()) > 1800 and a[0].shape[0] == 64
+    e = {"mel": (a[0] - b[0]).abs().max().item(), "postnet": (a[1] - b[1]).abs().max().item(), "tmax": int(a[9].max()),
+         "frames": int(a[9].sum())}
+    parity_log("fs2_full_size_libri_B64_tc_vs_exact", **e)
+    assert e["mel"] < 2e-4 and e["postnet"] < 2e-4, e          # each path is within ~3e-5 of the oracle at this length; bar 1e-3
+    # padded mel rows equal mel_linear.bias exactly (decoder output is zeroed there, SURVEY.md App. A.7)
+    bias = sd["mel_linear.bias"].to(DEV)
+    pad = a[7]                                             # True = padded frame
+    assert pad.any() and (a[0][pad] - bias).abs().max().item() < 1e-6
+    assert torch.isfinite(a[1]).all()
+
+
 def test_fastspeech2_frame_level_variances(scratch, parity_log):
     """pitch / energy feature = frame_level (config/LJSpeech_paper): predictors run on the expanded sequence."""
     import copy
