@@ -187,6 +187,22 @@ def test_hifigan_vs_oracle(B, T, parity_log):
     assert (gen(view).cpu() - want).abs().max() < WAV_TOL
 
 
+def test_hifigan_full_size_tensor_core_vs_exact_path(parity_log):
+    """BASELINE.json configs[2]'s vocoder at FULL size (B = 16 x 1012 frames -> 16 x 259072 samples; the CPU oracle needs about a
+    minute per utterance): the tcgen05 path against the exact-fp32 kernels that the small cases above pin to the oracle."""
+    gen, _ = _generator(seed=5)
+    mel = synth.make_mel(16, 1012, seed=6).to(DEV)
+    got = gen(mel)
+    gen.use_tensor_cores = False; gen._invalidate()
+    exact = gen(mel)
+    gen.use_tensor_cores = True; gen._invalidate()
+    torch.cuda.synchronize()
+    assert got.shape == (16, 1, 1012 * 256) and torch.isfinite(got).all()
+    err, peak = (got - exact).abs().max().item(), exact.abs().max().item()
+    parity_log("hifigan_full_size_B16_T1012_tc_vs_exact", wav_tc_vs_exact=err, peak=peak)
+    assert err < WAV_TOL and peak > 0.3, (err, peak)
+
+
 def test_hifigan_golden_vs_reference():
     import numpy as np, os
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hifigan.npz"))
