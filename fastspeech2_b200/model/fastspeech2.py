@@ -49,7 +49,7 @@ class FastSpeech2(nn.Module):
                         torch.exp(torch.linspace(np.log(stats["energy"][0]), np.log(stats["energy"][1]), n)))
         self.multi_speaker = bool(model_config["multi_speaker"])
         self.max_seq_len = int(model_config["max_seq_len"])
-        # Which sub-networks may run on the 3xTF32 tensor-core kernel.  Encoder and predictors stay on the exact fp32 kernels:
+        # Which sub-networks may run on the split-FP16 tcgen05 kernel.  Encoder and predictors stay on the exact fp32 kernels:
         # they feed the discrete duration / pitch-bucket decisions (hard part 2) and are <1% of the FLOPs.
         self.tc_mask = L.TC_DECODER | L.TC_POSTNET
         self._packed = None          # (AcousticModel struct, keep-alive tensors, device)

@@ -43,7 +43,7 @@ enum {
 
 enum { FS2_ACT_NONE = 0, FS2_ACT_RELU = 1, FS2_ACT_TANH = 2, FS2_ACT_LRELU = 3 };
 enum { FS2_CONV_AUTO = 0, FS2_CONV_SIMT = 1, FS2_CONV_TC = 2 };
-/* which parts of the acoustic model may use the 3xTF32 tensor-core kernel (fs2_acoustic_model.tc_mask) */
+/* which parts of the acoustic model may use the split-FP16 tcgen05 kernel (fs2_acoustic_model.tc_mask) */
 enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POSTNET = 8 };
 
 /* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per work item,
@@ -64,7 +64,11 @@ int fs2_conv_tc_block(int N); /* 0 when N is not supported by the tensor-core ke
 /* y[b,t,n] = (accumulate ? y : 0) + alpha * ( out_act( bias[n] + sum_{j<taps} sum_c in_act(x[b, t + j*dilation - pad_left, c]) * w[j][c][n] ) + res[b,t,n] )
  * rows outside [0,T) read as zero (Conv1d zero padding); rows t >= row_lens[b] are written as exact 0 when row_lens != NULL.
  * Strides are in elements.  Covers nn.Linear (taps=1), nn.Conv1d (any odd k, dilation), and one phase group of
- * ConvTranspose1d (two taps, y_row_stride = u*C_out; see fs2_vocoder_model). */
+ * ConvTranspose1d (two taps, y_row_stride = u*C_out; see fs2_vocoder_model).
+ * Both kernels: Cin % 16 == 0, pointers 16-byte aligned, strides % 4 == 0.  The tcgen05 kernel additionally needs w_tc,
+ * N % 16 == 0, x 32-byte aligned with x strides % 8 == 0 (256-bit loads), in_act in {NONE, LRELU with 0 <= slope <= 1} and
+ * (taps-1)*dilation <= 256; anything else is served by the exact kernel under FS2_CONV_AUTO and refused (FS2_ERR_UNSUPPORTED)
+ * under FS2_CONV_TC.  Activations beyond +-65504 saturate in the fp16 hi/lo split of the tcgen05 kernel. */
 typedef struct fs2_conv1d_args {
   const float* x; int64_t x_batch_stride, x_row_stride;
   int B, T, Cin;
@@ -72,8 +76,8 @@ typedef struct fs2_conv1d_args {
   const float* bias; /* [N] or NULL */
   int N, taps, dilation, pad_left;
   const float* w_tc; /* NULL, or the same weights in the tcgen05 tile layout (see "tensor-core weight tiles" below) */
-  int backend;       /* FS2_CONV_AUTO: tcgen05 3xTF32 kernel when w_tc is given and the shape qualifies, else the fp32 CUDA-core kernel */
-  unsigned tc_variant; /* 0; debug knob for descriptor bring-up */
+  int backend;       /* FS2_CONV_AUTO: split-FP16 tcgen05 kernel when w_tc is given and the shape qualifies, else the fp32 CUDA-core kernel */
+  unsigned tc_variant; /* 0; reserved (A/B experiments) */
   int in_act; float in_slope;
   int out_act; float out_slope;
   const float* res; int64_t res_batch_stride, res_row_stride; /* NULL = none */
