@@ -40,33 +40,11 @@ int g_tc_pdl = 0;                  // programmatic dependent launch: 0 = off (de
                                    // stays off; debug switch fs2_debug_set_tc_pdl
 int g_tc_tune[4] = {0, 0, 0, 0};   // debug overrides: SA, SB, TPS, grid (0 = heuristic); set through fs2_debug_set_tc_tuning
 
-// `wt` must be the tiled layout produced by fastspeech2_b200.packing.pack_conv_tc (see fs2b200.h)
-int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s, long long wt_batch_stride) {
-  if (!a || !a->x || !wt || !a->y) return FS2_ERR_ARG;
-  if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
-  if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
-  if (!aligned16(a->x) || !aligned16(wt) || !aligned16(a->y) || (a->res && !aligned16(a->res))) return FS2_ERR_ARG;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    const int mx = 227 * 1024;
-    if (e == cudaSuccess) e = conv_tc_prepare_mt1(mx);
-    if (e == cudaSuccess) e = conv_tc_prepare_mt2(mx);
-    if (e == cudaSuccess) e = conv_tc_prepare_mt4(mx);
-    if (e != cudaSuccess) { g_num_sms = 0; return FS2_ERR_CUDA - (int)e; }
-  }
-  TcP p;
-  p.x = a->x; p.xbs = a->x_batch_stride; p.xrs = a->x_row_stride;
-  p.B = a->B; p.T = a->T; p.Cin = a->Cin;
-  p.wt = wt; p.wt_bstride = wt_batch_stride; p.bias = a->bias; p.N = a->N; p.NB = conv_tc_nb(a->N);
-  p.taps = a->taps; p.dil = a->dilation; p.pad = a->pad_left;
-  p.in_act = a->in_act; p.in_slope = a->in_slope; p.out_act = a->out_act; p.out_slope = a->out_slope;
-  p.res = a->res; p.rbs = a->res_batch_stride; p.rrs = a->res_row_stride;
-  p.alpha = a->alpha; p.accumulate = a->accumulate; p.row_lens = a->row_lens;
-  p.y = a->y; p.ybs = a->y_batch_stride; p.yrs = a->y_row_stride;
-  p.trace = g_tc_trace;
-  p.variant = variant;
+// Shape-derived launch plan (pure host logic, no CUDA calls): work-item shape, accumulator grouping, ring depths, shared /
+// tensor memory budget, grid.  Returns FS2_OK or FS2_ERR_UNSUPPORTED.  Exposed as fs2_conv_tc_plan so that the heuristics'
+// invariants are testable without a GPU (tests/test_abi.py).
+static int conv_tc_plan(const fs2_conv1d_args* a, int num_sms, TcP& p, size_t& smem, int& grid) {
+  p.NB = conv_tc_nb(a->N);
   p.acc_stride = (p.NB + 31) & ~31;
   const int halo = (a->taps - 1) * a->dilation;
   const int tiles128 = (a->T + 127) / 128;
@@ -76,7 +54,7 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   if (mt > tiles128) mt = tiles128 >= 2 ? 2 : 1;
   if (mt == 2 && mt * 128 + halo > TC_LD * TC_TTHREADS / TC_CHUNKS) mt = 1;   // rows one register-ring slot can hold
   // small problems (decoder projections, attention PV): prefer more, smaller work items when MT = 2 would leave SMs idle
-  if (mt == 2 && 2LL * (a->N / p.NB) * a->B * ((a->T + 255) / 256) <= g_num_sms) mt = 1;   // measured: helps at <= 1/2 wave, hurts K-heavy layers at ~1 wave
+  if (mt == 2 && 2LL * (a->N / p.NB) * a->B * ((a->T + 255) / 256) <= num_sms) mt = 1;   // measured: helps at <= 1/2 wave, hurts K-heavy layers at ~1 wave
   int R = mt * 128 + halo;
   R += (12 - (R & 7)) & 7;                             // R % 8 == 4: conflict-free transform stores (2 chunks per row)
   p.MT = mt; p.R = R;
@@ -109,15 +87,64 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   if (g_tc_tune[1] > 0) sb = g_tc_tune[1] > TC_SB_MAX ? TC_SB_MAX : g_tc_tune[1];
   if (fixed + sa * a_stage + sb * b_stage > budget) return FS2_ERR_UNSUPPORTED;
   p.SA = sa; p.SB = sb;
-  const size_t smem = fixed + sa * a_stage + sb * b_stage;
+  smem = fixed + sa * a_stage + sb * b_stage;
   p.tmem_cols = pow2_cols(2 * mt * p.TG * p.acc_stride);
   p.tiles_per_batch = (a->T + mt * 128 - 1) / (mt * 128);
   const long long n_items = (long long)(a->N / p.NB) * a->B * p.tiles_per_batch;
   if (n_items > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   p.n_items = (int)n_items;
-  p.pdl = g_tc_pdl == 2 || (g_tc_pdl == 1 && n_items <= 4LL * g_num_sms);
-  int grid = n_items < g_num_sms ? (int)n_items : g_num_sms;
+  p.pdl = g_tc_pdl == 2 || (g_tc_pdl == 1 && n_items <= 4LL * num_sms);
+  grid = n_items < num_sms ? (int)n_items : num_sms;
   if (g_tc_tune[3] > 0 && g_tc_tune[3] < grid) grid = g_tc_tune[3];
+  return FS2_OK;
+}
+
+// out[12] = {NB, MT, TG, SA, SB, TPS, R, tmem_cols, tiles_per_batch, n_items, grid, dynamic smem bytes}
+int conv_tc_plan_query(const fs2_conv1d_args* a, int num_sms, int* out) {
+  if (!a || !out || num_sms <= 0 || a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
+  if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
+  TcP p{};
+  size_t smem = 0;
+  int grid = 0;
+  const int rc = conv_tc_plan(a, num_sms, p, smem, grid);
+  if (rc != FS2_OK) return rc;
+  const int v[12] = {p.NB, p.MT, p.TG, p.SA, p.SB, p.TPS, p.R, p.tmem_cols, p.tiles_per_batch, p.n_items, grid, (int)smem};
+  for (int i = 0; i < 12; i++) out[i] = v[i];
+  return FS2_OK;
+}
+
+// `wt` must be the tiled layout produced by fastspeech2_b200.packing.pack_conv_tc (see fs2b200.h)
+int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s, long long wt_batch_stride) {
+  if (!a || !a->x || !wt || !a->y) return FS2_ERR_ARG;
+  if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
+  if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
+  if (!aligned16(a->x) || !aligned16(wt) || !aligned16(a->y) || (a->res && !aligned16(a->res))) return FS2_ERR_ARG;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const int mx = 227 * 1024;
+    if (e == cudaSuccess) e = conv_tc_prepare_mt1(mx);
+    if (e == cudaSuccess) e = conv_tc_prepare_mt2(mx);
+    if (e == cudaSuccess) e = conv_tc_prepare_mt4(mx);
+    if (e != cudaSuccess) { g_num_sms = 0; return FS2_ERR_CUDA - (int)e; }
+  }
+  TcP p{};
+  p.x = a->x; p.xbs = a->x_batch_stride; p.xrs = a->x_row_stride;
+  p.B = a->B; p.T = a->T; p.Cin = a->Cin;
+  p.wt = wt; p.wt_bstride = wt_batch_stride; p.bias = a->bias; p.N = a->N;
+  p.taps = a->taps; p.dil = a->dilation; p.pad = a->pad_left;
+  p.in_act = a->in_act; p.in_slope = a->in_slope; p.out_act = a->out_act; p.out_slope = a->out_slope;
+  p.res = a->res; p.rbs = a->res_batch_stride; p.rrs = a->res_row_stride;
+  p.alpha = a->alpha; p.accumulate = a->accumulate; p.row_lens = a->row_lens;
+  p.y = a->y; p.ybs = a->y_batch_stride; p.yrs = a->y_row_stride;
+  p.trace = g_tc_trace;
+  p.variant = variant;
+  size_t smem = 0;
+  int grid = 0;
+  const int rc = conv_tc_plan(a, g_num_sms, p, smem, grid);
+  if (rc != FS2_OK) return rc;
+  const int mt = p.MT;
   prof_before(s);
   if (mt == 4) conv_tc_launch_mt4(p, (unsigned)grid, smem, s);
   else if (mt == 2) conv_tc_launch_mt2(p, (unsigned)grid, smem, s);

@@ -35,6 +35,7 @@ int attention_gemm(const fs2_attention_args* a, void* ws, size_t ws_bytes, cudaS
 size_t attention_gemm_workspace(int B, int T, int H);
 bool conv_tc_supported(const fs2_conv1d_args* a);
 int conv_tc_nb(int N);
+int conv_tc_plan_query(const fs2_conv1d_args* a, int num_sms, int* out);
 extern long long* g_tc_trace;
 extern int g_tc_tune[4];
 extern int g_tc_pdl;
@@ -328,6 +329,7 @@ extern "C" {
 
 int fs2_abi_version(void) { return 4; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
+int fs2_conv_tc_plan(const fs2_conv1d_args* a, int num_sms, int32_t* out) { return conv_tc_plan_query(a, num_sms, out); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count.load(); }
 size_t fs2_struct_size(int which) {
   switch (which) {

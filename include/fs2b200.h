@@ -52,6 +52,12 @@ enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POS
  * i.e. every (K-block, tap) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major, fp16), fetched by one
  * cp.async.bulk.  fastspeech2_b200/packing.py::pack_conv_tc builds it. */
 int fs2_conv_tc_block(int N); /* 0 when N is not supported by the tensor-core kernel */
+struct fs2_conv1d_args;
+/* Launch plan the tcgen05 kernel would use for this call on a device with num_sms SMs (pure host logic, no CUDA call, pointers are
+ * only checked for alignment): out[12] = {NB, MT (128-row tiles per work item), TG (accumulators per tile), slab stages, weight
+ * stages, taps per weight stage, slab rows, TMEM columns, work items per utterance, work items, grid, dynamic shared memory bytes}.
+ * Returns FS2_ERR_UNSUPPORTED for shapes the kernel does not take. */
+int fs2_conv_tc_plan(const struct fs2_conv1d_args* a, int num_sms, int32_t* out);
 
 #define FS2_MAX_LAYERS 12
 #define FS2_MAX_POSTNET 8

@@ -56,6 +56,53 @@ def test_host_side_argument_checks_need_no_gpu():
     assert h.fs2_encode_workspace_bytes(ctypes.byref(m), 0, 5) == 0
 
 
+def _plan(h, B, T, Cin, N, taps, dil=1, num_sms=148, x=0x1000, x_row_stride=None):
+    a = _lib.Conv1dArgs(x=x, x_batch_stride=T * (x_row_stride or Cin), x_row_stride=x_row_stride or Cin, B=B, T=T, Cin=Cin, w=0x1000, N=N, taps=taps,
+                        dilation=dil, pad_left=(taps - 1) * dil // 2, w_tc=0x1000, y=0x1000, y_batch_stride=T * N, y_row_stride=N, alpha=1.0)
+    out = (ctypes.c_int32 * 12)()
+    rc = h.fs2_conv_tc_plan(ctypes.byref(a), num_sms, out)
+    keys = ("NB", "MT", "TG", "SA", "SB", "TPS", "R", "tmem_cols", "tiles_per_batch", "n_items", "grid", "smem")
+    return rc, dict(zip(keys, out))
+
+
+def test_tcgen05_launch_plan_respects_the_hardware_limits():
+    """Host-side heuristics of the tcgen05 conv (work-item shape, ring depths, TMEM / shared-memory budget) for every layer shape of
+    both models at the BASELINE batch sizes, plus a sweep: no plan may exceed 227 KB of shared memory, 512 TMEM columns, the
+    register-ring row capacity or the ring maxima, and the work items must cover the problem exactly."""
+    h = _lib.lib()
+    shapes = []
+    for B, T in ((1, 7), (1, 1012), (16, 1012), (64, 2032)):
+        shapes += [(B, T, 256, 768, 1, 1), (B, T, 256, 256, 1, 1), (B, T, 256, 1024, 9, 1), (B, T, 1024, 256, 1, 1), (B, T, 256, 80, 1, 1),
+                   (B, T, 80, 512, 5, 1), (B, T, 512, 512, 5, 1), (B, T, 512, 80, 5, 1), (B, T, 128, 2048, 1, 1), (B, T, 2048, 128, 1, 1)]
+        t, c = T, 512
+        shapes.append((B, T, 80, 512, 7, 1))                                   # conv_pre
+        for u in (8, 8, 2, 2):
+            shapes.append((B, t, c, (u // 2) * (c // 2), 2, 1))                # one ConvTranspose phase group
+            t, c = t * u, c // 2
+            shapes += [(B, t, c, c, k, d) for k in (3, 7, 11) for d in (1, 3, 5)]
+    for (B, T, Cin, N, k, d) in shapes:
+        rc, p = _plan(h, B, T, Cin, N, k, d)
+        assert rc == 0, (B, T, Cin, N, k, d, rc)
+        assert p["NB"] % 16 == 0 and 16 <= p["NB"] <= 128 and N % p["NB"] == 0
+        assert p["MT"] in (1, 2, 4) and p["TG"] in (1, 2)
+        acc_stride = (p["NB"] + 31) // 32 * 32
+        assert 2 * p["MT"] * p["TG"] * acc_stride <= p["tmem_cols"] <= 512 and p["tmem_cols"] & (p["tmem_cols"] - 1) == 0
+        assert p["smem"] <= 227 * 1024
+        assert 2 <= p["SA"] <= 8 and 2 <= p["SB"] <= 8 and 1 <= p["TPS"] <= k
+        assert p["R"] % 8 == 4 and p["R"] >= p["MT"] * 128 + (k - 1) * d
+        assert p["R"] <= (5 if p["MT"] == 4 else 3) * 256 // 2 + 7               # rows the transform warps' register ring can hold
+        assert p["tiles_per_batch"] * p["MT"] * 128 >= T > (p["tiles_per_batch"] - 1) * p["MT"] * 128
+        assert p["n_items"] == (N // p["NB"]) * B * p["tiles_per_batch"] and p["grid"] == min(p["n_items"], 148)
+    # the measured shape classes keep their tuned plans (profiles/r01_tc_tune_sa.txt, r01_tc_ab_mt4.txt)
+    assert _plan(h, 16, 259072, 32, 32, 3)[1]["MT"] == 4 and _plan(h, 16, 259072, 32, 32, 3)[1]["SA"] == 3
+    assert _plan(h, 16, 64768, 128, 128, 3)[1]["SA"] == 5 and _plan(h, 16, 64768, 128, 128, 11, 5)[1]["TPS"] == 4
+    assert _plan(h, 16, 1012, 1024, 128, 1)[1]["MT"] == 1                       # half a wave of MT=2 items: smaller items
+    # refused shapes: C_in % 16, N % 16, misaligned or oddly strided x, halo beyond the slab
+    assert _plan(h, 1, 128, 24, 16, 1)[0] == -2 and _plan(h, 1, 128, 16, 24, 1)[0] == -2
+    assert _plan(h, 1, 128, 16, 16, 1, x=0x1010)[0] == -2 and _plan(h, 1, 128, 16, 16, 1, x_row_stride=20)[0] == -2
+    assert _plan(h, 1, 4096, 16, 16, 11, 30)[0] == -2
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "fastspeech2_b200")
     for dirpath, _, files in os.walk(pkg):
