@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--phonemes", type=int, default=128)
     ap.add_argument("--cpu-sample", type=int, default=2, help="utterances in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--voc-f8-mask", type=int, default=None, help="override hifigan.Generator.f8_mask (A/B of the operand split)")
+    ap.add_argument("--fs2-f8", type=int, default=None, choices=[0, 1], help="override the decoder / PostNet operand split (A/B)")
     return ap.parse_args()
 
 
@@ -196,9 +198,14 @@ def run_ours(args):
     pc, mc = configs.make_configs("LJSpeech", tempfile.mkdtemp())
     model = FastSpeech2(pc, mc)
     model.load_state_dict(synth.fastspeech2_state_dict(pc, mc, seed=0))
+    if args.fs2_f8 is not None:
+        f8_bits = _lib.TC_DECODER_F8 | _lib.TC_POSTNET_F8
+        model.tc_mask = (model.tc_mask & ~f8_bits) | (f8_bits if args.fs2_f8 else 0)
     model = model.to(dev).eval()
     voc = Generator(AttrDict(configs.HIFIGAN_CONFIG))
     voc.load_state_dict(synth.hifigan_state_dict(configs.HIFIGAN_CONFIG, seed=0))
+    if args.voc_f8_mask is not None:
+        voc.f8_mask = args.voc_f8_mask
     voc.eval()
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -334,6 +341,7 @@ def run_ours(args):
                           "fastspeech2_only_mel_frames_per_s": mel_fps, "fastspeech2_only_ms_per_step": ms_mel / args.steps,
                           "algorithmic_tflop_per_step": (FS2_FLOPS(args.phonemes, frames_step / (args.batch * world)) * args.batch * world
                                                          + HIFIGAN_FLOPS_PER_FRAME * frames_step) / 1e12,
+                          "operand_split": {"vocoder_f8_mask": int(voc.f8_mask), "fs2_tc_mask": int(model.tc_mask)},
                           "build": lib.fs2_build_info().decode()}}
         print(json.dumps(line), flush=True)
     if world > 1:

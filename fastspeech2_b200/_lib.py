@@ -11,11 +11,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LAYERS, MAX_POSTNET, MAX_STAGES, MAX_RESBLOCKS, MAX_DIL = 12, 8, 8, 32, 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
 TC_ENCODER, TC_PREDICTORS, TC_DECODER, TC_POSTNET = 1, 2, 4, 8
+TC_DECODER_F8, TC_POSTNET_F8 = 16, 32
+TC_VARIANT_F8 = 1
 
 fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 i32, i64, f32 = C.c_int, C.c_int64, C.c_float
@@ -124,7 +126,8 @@ class VocoderModel(C.Structure):
                 ("w_rb2", (fp * MAX_DIL) * MAX_RESBLOCKS), ("b_rb2", (fp * MAX_DIL) * MAX_RESBLOCKS),
                 ("w_post", fp), ("b_post", fp),
                 ("w_pre_tc", fp), ("w_up_a_tc", fp * MAX_STAGES), ("w_up_b_tc", fp * MAX_STAGES),
-                ("w_rb1_tc", (fp * MAX_DIL) * MAX_RESBLOCKS), ("w_rb2_tc", (fp * MAX_DIL) * MAX_RESBLOCKS)]
+                ("w_rb1_tc", (fp * MAX_DIL) * MAX_RESBLOCKS), ("w_rb2_tc", (fp * MAX_DIL) * MAX_RESBLOCKS),
+                ("f8_mask", i32)]
 
 
 class VocoderArgs(C.Structure):

@@ -19,8 +19,13 @@ _STATS = {
                  "energy": [-1.431044578552246, 8.184337615966797, 37.32621679053821, 26.044180782835863]},
     "LibriTTS": {"pitch": [-2.646310080183867, 11.922013280384945, 163.55966796034886, 61.80669044989039],
                  "energy": [-1.248658537864685, 9.75546646118164, 41.65338755249414, 33.35850956918866]},
+    # config/LJSpeech_paper: pitch / energy NOT normalised (preprocess.yaml:27,30), so the bin edges are raw Hz / energy.  The
+    # reference ships no preprocessed_data/LJSpeech_paper/stats.json; these are representative raw LJSpeech ranges (synthetic
+    # fixture values: only positivity of the pitch minimum matters for the log-spaced edges, model/modules.py:48-54).
+    "LJSpeech_paper": {"pitch": [71.0, 795.8, 207.6309860026605, 46.77559025098988],
+                       "energy": [0.0185, 314.96, 37.32621679053821, 26.044180782835863]},
 }
-_N_SPEAKERS = {"LJSpeech": 1, "LibriTTS": 904}
+_N_SPEAKERS = {"LJSpeech": 1, "LibriTTS": 904, "LJSpeech_paper": 1}
 
 _MODEL = {
     "transformer": {"encoder_layer": 4, "encoder_head": 2, "encoder_hidden": 256,
@@ -68,4 +73,9 @@ def make_configs(dataset: str, scratch_dir: str):
     model["multi_speaker"] = n_spk > 1
     if dataset == "LibriTTS":
         model["vocoder"]["speaker"] = "universal"
+    if dataset == "LJSpeech_paper":                    # config/LJSpeech_paper/{model,preprocess}.yaml
+        model["transformer"]["decoder_layer"] = 4
+        model["variance_embedding"]["pitch_quantization"] = "log"
+        for k in ("pitch", "energy"):
+            preprocess["preprocessing"][k] = {"feature": "frame_level", "normalization": False}
     return preprocess, model

@@ -140,6 +140,7 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.y = a->y; p.ybs = a->y_batch_stride; p.yrs = a->y_row_stride;
   p.trace = g_tc_trace;
   p.variant = variant;
+  p.f8 = (variant & FS2_TC_VARIANT_F8) ? 1 : 0;
   size_t smem = 0;
   int grid = 0;
   const int rc = conv_tc_plan(a, g_num_sms, p, smem, grid);

@@ -74,6 +74,7 @@ struct TcP {
   long long* trace;                // debug: [CTA][16 items][8] globaltimer stamps, or NULL
   unsigned variant;                // reserved for A/B experiments (unused by the shipped kernel)
   int pdl;                         // launched with programmatic stream serialisation: wait for the previous grid before touching its data
+  int f8;                          // operand split: 0 = three kind::f16 MMAs (hi*hi + lo*hi + hi*lo), 1 = kind::f16 main term + ONE kind::f8f6f4 correction MMA
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -123,6 +124,15 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 with E4M3 operands (K = 32 per instruction: here 16 channels x {activation-lo * weight-hi, activation-hi * weight-lo})
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -154,6 +164,13 @@ __device__ __forceinline__ uint32_t cvt_f16x2_sat(float a0, float a1) {
   uint32_t h;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(a1), "f"(a0));
   return h;
+}
+
+// e4m3x2 {byte 0 = a0, byte 1 = a1}, round-to-nearest, saturating at +-448
+__device__ __forceinline__ uint32_t cvt_e4m3x2_sat(float a0, float a1) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h) : "f"(a1), "f"(a0));
+  return (uint32_t)h;
 }
 
 // UMMA shared-memory descriptor, no-swizzle K-major: core matrix = 8 rows x 16 B stored contiguously (128 B);
@@ -342,10 +359,20 @@ __device__ __forceinline__ void tc_epilogue_dispatch(const TcP& p, uint32_t tmem
   }
 }
 
-// One K-block of one transform thread: input activation, fp16 hi/lo split, stores into the [chunk][row][8 halfs] slab planes.
-template <bool LRELU, int LD>
-__device__ __forceinline__ void tc_convert_store(const float (&src)[LD][8], const int (&rowu)[LD], const int (&offu)[LD], unsigned char* hi,
-                                                 unsigned char* lo, float in_slope) {
+// Operand scales of the f16 + f8 split (TcP::f8): activation lo * 2^12 and hi * 2 are rounded to E4M3; the packer stores
+// weight hi * 2^-12 and lo * 2^-1 in E4M3 (packing.pack_conv_tc), so both correction products carry the main term's scale.
+// |x| < 224 keeps the hi byte below E4M3's 448; beyond that the correction of that element saturates (the result degrades
+// towards single-pass fp16 accuracy for it, never to garbage).
+constexpr float TC_F8_LO_SCALE = 4096.f;
+constexpr float TC_F8_HI_SCALE = 2.f;
+
+// One K-block of one transform thread: input activation, operand split, stores into the slab planes.
+//   F8 = false: plane 0 = fp16 hi, plane 1 = fp16 lo, both [16-byte K-chunk of 8 channels][row][8 halfs].
+//   F8 = true : plane 0 = fp16 hi as above; plane 1 = E4M3 [chunk 0: lo of the 16 channels | chunk 1: hi of the 16 channels][row][16 bytes]
+//               -- the A operand of one K = 32 kind::f8f6f4 MMA whose B operand is [weight hi ; weight lo].
+template <bool LRELU, bool F8, int LD>
+__device__ __forceinline__ void tc_convert_store(const float (&src)[LD][8], const int (&rowu)[LD], const int (&offu)[LD], const int (&off8)[LD],
+                                                 unsigned char* hi, unsigned char* lo, uint32_t chunk_bytes, float in_slope) {
 #pragma unroll
   for (int u = 0; u < LD; u++) {
     if (rowu[u] < 0) continue;
@@ -359,10 +386,22 @@ __device__ __forceinline__ void tc_convert_store(const float (&src)[LD][8], cons
       }
       hw[j] = cvt_f16x2_sat(a0, a1);
       const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
-      lw[j] = cvt_f16x2_sat(a0 - hf.x, a1 - hf.y);     // a - hi is exact in fp32
+      if (F8) {
+        const uint32_t l8 = cvt_e4m3x2_sat((a0 - hf.x) * TC_F8_LO_SCALE, (a1 - hf.y) * TC_F8_LO_SCALE);   // a - hi is exact in fp32
+        const uint32_t h8 = cvt_e4m3x2_sat(hf.x * TC_F8_HI_SCALE, hf.y * TC_F8_HI_SCALE);
+        if (j & 1) { lw[j >> 1] |= l8 << 16; lw[2 + (j >> 1)] |= h8 << 16; }
+        else { lw[j >> 1] = l8; lw[2 + (j >> 1)] = h8; }
+      } else {
+        lw[j] = cvt_f16x2_sat(a0 - hf.x, a1 - hf.y);
+      }
     }
     *reinterpret_cast<uint4*>(hi + offu[u]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(lo + offu[u]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    if (F8) {
+      *reinterpret_cast<uint2*>(lo + off8[u]) = make_uint2(lw[0], lw[1]);                 // E4M3 lo of these 8 channels
+      *reinterpret_cast<uint2*>(lo + off8[u] + chunk_bytes) = make_uint2(lw[2], lw[3]);   // E4M3 hi of these 8 channels
+    } else {
+      *reinterpret_cast<uint4*>(lo + offu[u]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
   }
 }
 
@@ -475,15 +514,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
               const uint64_t ah0 = a_hi + row_off, al0 = a_lo + row_off;
               const uint32_t first = (kb | tap | j) ? 1u : 0u;
               // consecutive MMAs alternate between tiles / accumulator groups
+              if (p.f8) {
 #pragma unroll
-              for (int mt = 0; mt < MT; mt++)          // A_lo * B_hi
-                tc_mma_f16(d0 + mt * tile_cols + g_cross, al0 + mt * 128, b_hi, idesc, first);
+                for (int mt = 0; mt < MT; mt++)          // fp16: A_hi * B_hi
+                  tc_mma_f16(d0 + mt * tile_cols, ah0 + mt * 128, b_hi, idesc, first);
 #pragma unroll
-              for (int mt = 0; mt < MT; mt++)          // A_hi * B_hi
-                tc_mma_f16(d0 + mt * tile_cols, ah0 + mt * 128, b_hi, idesc, TG >= 2 ? first : 1u);
+                for (int mt = 0; mt < MT; mt++)          // E4M3, K = 32: [A_lo | A_hi] * [B_hi ; B_lo]
+                  tc_mma_f8(d0 + mt * tile_cols + g_cross, al0 + mt * 128, b_lo, idesc, TG >= 2 ? first : 1u);
+              } else {
 #pragma unroll
-              for (int mt = 0; mt < MT; mt++)          // A_hi * B_lo
-                tc_mma_f16(d0 + mt * tile_cols + g_cross, ah0 + mt * 128, b_lo, idesc, 1u);
+                for (int mt = 0; mt < MT; mt++)          // A_lo * B_hi
+                  tc_mma_f16(d0 + mt * tile_cols + g_cross, al0 + mt * 128, b_hi, idesc, first);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)          // A_hi * B_hi
+                  tc_mma_f16(d0 + mt * tile_cols, ah0 + mt * 128, b_hi, idesc, TG >= 2 ? first : 1u);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)          // A_hi * B_lo
+                  tc_mma_f16(d0 + mt * tile_cols + g_cross, ah0 + mt * 128, b_lo, idesc, 1u);
+              }
             }
             tc_commit(&emptyB[sb]);                    // weight stage free once these MMAs retire
           } else {
@@ -515,12 +563,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const bool lrelu_in = p.in_act == FS2_ACT_LRELU;
     const float in_slope = p.in_slope;
     // per-thread (row, chunk) slots: fixed for the whole kernel
-    int rowu[LD], offu[LD], goff[LD];
+    int rowu[LD], offu[LD], off8[LD], goff[LD];
 #pragma unroll
     for (int u = 0; u < LD; u++) {
       const int idx = u * TC_TTHREADS + wt;
       rowu[u] = idx < items ? (idx >> 1) : -1;
       offu[u] = (((idx & 1) * R) + (idx >> 1)) * 16;                  // smem byte offset inside a hi / lo plane
+      off8[u] = (idx >> 1) * 16 + (idx & 1) * 8;                      // f8 split: byte offset inside one 16-channel E4M3 chunk
       goff[u] = (idx >> 1) * (int)p.xrs + (idx & 1) * 8;              // global float offset from the slab's first row
     }
     // load cursor (runs TC_DEPTH K-blocks ahead of the store cursor); no divisions on the per-K-block path
@@ -576,8 +625,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
 #endif
           mbar_wait(&emptyA[ra.idx], ra.phase ^ 1);
           unsigned char* hi = a_base + (size_t)ra.idx * 2 * a_plane;
-          if (lrelu_in) tc_convert_store<true, LD>(v[d], rowu, offu, hi, hi + a_plane, in_slope);
-          else tc_convert_store<false, LD>(v[d], rowu, offu, hi, hi + a_plane, in_slope);
+          if (p.f8) {
+            if (lrelu_in) tc_convert_store<true, true, LD>(v[d], rowu, offu, off8, hi, hi + a_plane, (uint32_t)R * 16, in_slope);
+            else tc_convert_store<false, true, LD>(v[d], rowu, offu, off8, hi, hi + a_plane, (uint32_t)R * 16, in_slope);
+          } else {
+            if (lrelu_in) tc_convert_store<true, false, LD>(v[d], rowu, offu, off8, hi, hi + a_plane, (uint32_t)R * 16, in_slope);
+            else tc_convert_store<false, false, LD>(v[d], rowu, offu, off8, hi, hi + a_plane, (uint32_t)R * 16, in_slope);
+          }
           fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(&fullA[ra.idx]);   // one arrival per transform warp

@@ -77,9 +77,9 @@ struct Arena {
 static int conv(cudaStream_t s, const float* x, int B, int T, int Cin, const float* w, const float* w_tc, const float* bias, int N,
                 int taps, int dil, int pad, int out_act, float out_slope, float* y, const float* res = nullptr,
                 int in_act = FS2_ACT_NONE, float in_slope = 0.f, float alpha = 1.f, int accumulate = 0,
-                const int32_t* row_lens = nullptr) {
+                const int32_t* row_lens = nullptr, unsigned tc_variant = 0) {
   fs2_conv1d_args a{};
-  a.w_tc = w_tc; a.backend = FS2_CONV_AUTO;
+  a.w_tc = w_tc; a.backend = FS2_CONV_AUTO; a.tc_variant = tc_variant;
   a.x = x; a.x_batch_stride = (int64_t)T * Cin; a.x_row_stride = Cin;
   a.B = B; a.T = T; a.Cin = Cin;
   a.w = w; a.bias = bias; a.N = N; a.taps = taps; a.dilation = dil; a.pad_left = pad;
@@ -99,10 +99,11 @@ struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; void* att_ws; size_t att_byte
 
 // One FFT block in place on bufs.x  (transformer/Layers.py:21-30)
 static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_block_weights& w, const FftBufs& f, int B, int T,
-                     const int32_t* lens, bool tc) {
+                     const int32_t* lens, bool tc, unsigned tcv) {
   const int D = m->d_model, F = m->d_inner;
   const float* none = nullptr;
-  FS2_TRY(conv(s, f.x, B, T, D, w.w_qkv, tc ? w.w_qkv_tc : none, w.b_qkv, 3 * D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.qkv));
+  FS2_TRY(conv(s, f.x, B, T, D, w.w_qkv, tc ? w.w_qkv_tc : none, w.b_qkv, 3 * D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.qkv, nullptr, FS2_ACT_NONE, 0.f,
+               1.f, 0, nullptr, tcv));
   fs2_attention_args at{};
   at.qkv = f.qkv; at.ctx = f.ctx; at.B = B; at.T = T; at.H = m->n_head; at.Dh = D / m->n_head; at.key_lens = lens;
   at.scale = 1.0f / sqrtf((float)(D / m->n_head));
@@ -111,10 +112,13 @@ static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_
   } else {
     FS2_TRY(attention_simt(&at, s));
   }
-  FS2_TRY(conv(s, f.ctx, B, T, D, w.w_o, tc ? w.w_o_tc : none, w.b_o, D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.tmp, f.x));
+  FS2_TRY(conv(s, f.ctx, B, T, D, w.w_o, tc ? w.w_o_tc : none, w.b_o, D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.tmp, f.x, FS2_ACT_NONE, 0.f, 1.f, 0, nullptr,
+               tcv));
   FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln1_g, w.ln1_b, lens));
-  FS2_TRY(conv(s, f.x, B, T, D, w.w_1, tc ? w.w_1_tc : none, w.b_1, F, m->k1, 1, (m->k1 - 1) / 2, FS2_ACT_RELU, 0.f, f.hid));
-  FS2_TRY(conv(s, f.hid, B, T, F, w.w_2, tc ? w.w_2_tc : none, w.b_2, D, m->k2, 1, (m->k2 - 1) / 2, FS2_ACT_NONE, 0.f, f.tmp, f.x));
+  FS2_TRY(conv(s, f.x, B, T, D, w.w_1, tc ? w.w_1_tc : none, w.b_1, F, m->k1, 1, (m->k1 - 1) / 2, FS2_ACT_RELU, 0.f, f.hid, nullptr, FS2_ACT_NONE,
+               0.f, 1.f, 0, nullptr, tcv));
+  FS2_TRY(conv(s, f.hid, B, T, F, w.w_2, tc ? w.w_2_tc : none, w.b_2, D, m->k2, 1, (m->k2 - 1) / 2, FS2_ACT_NONE, 0.f, f.tmp, f.x, FS2_ACT_NONE,
+               0.f, 1.f, 0, nullptr, tcv));
   FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln2_g, w.ln2_b, lens));
   return FS2_OK;
 }
@@ -169,7 +173,7 @@ static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cu
 
   fs2_embed_args e{a->texts, m->word_emb, m->enc_pos, f.x, B, L, D, m->n_vocab};
   FS2_TRY(embed_positions(&e, s));
-  for (int i = 0; i < m->n_enc; i++) FS2_TRY(fft_block(s, m, m->enc[i], f, B, L, a->src_lens, (m->tc_mask & FS2_TC_ENCODER) != 0));
+  for (int i = 0; i < m->n_enc; i++) FS2_TRY(fft_block(s, m, m->enc[i], f, B, L, a->src_lens, (m->tc_mask & FS2_TC_ENCODER) != 0, 0));
   if (m->spk_emb) {
     if (!a->speakers) return FS2_ERR_ARG;
     fs2_rowbias_args r{f.x, m->spk_emb, a->speakers, B, L, D, m->n_speakers};
@@ -236,9 +240,12 @@ static int decode_impl(const fs2_acoustic_model* m, const fs2_decode_args* a, cu
     }
     FS2_TRY(add_positions(f.x, m->dec_pos, B, T, D, s));
   }
-  for (int i = 0; i < m->n_dec; i++) FS2_TRY(fft_block(s, m, m->dec[i], f, B, T, a->mel_mask_lens, (m->tc_mask & FS2_TC_DECODER) != 0));
+  for (int i = 0; i < m->n_dec; i++) FS2_TRY(fft_block(s, m, m->dec[i], f, B, T, a->mel_mask_lens, (m->tc_mask & FS2_TC_DECODER) != 0,
+                                                     (m->tc_mask & FS2_TC_DECODER_F8) ? FS2_TC_VARIANT_F8 : 0));
   const bool tcp = (m->tc_mask & FS2_TC_POSTNET) != 0;
-  FS2_TRY(conv(s, f.x, B, T, D, m->w_mel, tcp ? m->w_mel_tc : nullptr, m->b_mel, m->n_mel, 1, 1, 0, FS2_ACT_NONE, 0.f, a->mel));
+  const unsigned tcpv = (m->tc_mask & FS2_TC_POSTNET_F8) ? FS2_TC_VARIANT_F8 : 0;
+  FS2_TRY(conv(s, f.x, B, T, D, m->w_mel, tcp ? m->w_mel_tc : nullptr, m->b_mel, m->n_mel, 1, 1, 0, FS2_ACT_NONE, 0.f, a->mel, nullptr, FS2_ACT_NONE,
+               0.f, 1.f, 0, nullptr, tcpv));
   // PostNet: eval BatchNorm folded into (w, b) by the packer; unmasked, tanh on all but the last (Layers.py:129-137)
   const float* cur = a->mel;
   for (int i = 0; i < m->n_postnet; i++) {
@@ -246,7 +253,7 @@ static int decode_impl(const fs2_acoustic_model* m, const fs2_decode_args* a, cu
     float* dst = last ? a->postnet_mel : ((i & 1) ? pb : pa);
     FS2_TRY(conv(s, cur, B, T, m->post_cin[i], m->w_post[i], tcp ? m->w_post_tc[i] : nullptr, m->b_post[i], m->post_cout[i], m->post_k, 1,
                  (m->post_k - 1) / 2,
-                 last ? FS2_ACT_NONE : FS2_ACT_TANH, 0.f, dst, last ? a->mel : nullptr));
+                 last ? FS2_ACT_NONE : FS2_ACT_TANH, 0.f, dst, last ? a->mel : nullptr, FS2_ACT_NONE, 0.f, 1.f, 0, nullptr, tcpv));
     cur = dst;
   }
   return FS2_OK;
@@ -277,7 +284,7 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
     fs2_conv1d_args c{};
     c.x = a->mel; c.x_batch_stride = a->mel_batch_stride; c.x_row_stride = a->mel_row_stride;
     c.B = B; c.T = T; c.Cin = m->n_mel; c.w = m->w_pre; c.w_tc = m->w_pre_tc; c.bias = m->b_pre; c.N = m->c0; c.taps = 7;
-    c.dilation = 1; c.pad_left = 3;
+    c.dilation = 1; c.pad_left = 3; c.tc_variant = (m->f8_mask & 1) ? FS2_TC_VARIANT_F8 : 0;
     c.alpha = 1.f; c.y = bx; c.y_batch_stride = (int64_t)T * m->c0; c.y_row_stride = m->c0;
     FS2_TRY(conv1d_dispatch(&c, s));
   }
@@ -286,6 +293,7 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
   for (int i = 0; i < m->n_stages; i++) {
     const int u = m->rates[i], Co = C / 2;
     if (m->up_k[i] != 2 * u || (u & 1)) return FS2_ERR_UNSUPPORTED;
+    const unsigned tcv = (m->f8_mask & (2 << i)) ? FS2_TC_VARIANT_F8 : 0;
     // ---- lrelu + ConvTranspose1d as two 2-tap phase-group convolutions (hifigan/models.py:152-153)
     for (int g = 0; g < 2; g++) {
       fs2_conv1d_args c{};
@@ -294,7 +302,7 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
       c.w_tc = g == 0 ? m->w_up_a_tc[i] : m->w_up_b_tc[i];
       c.bias = m->b_up[i] + (size_t)g * (u / 2) * Co;
       c.N = (u / 2) * Co; c.taps = 2; c.dilation = 1; c.pad_left = g == 0 ? 1 : 0;
-      c.in_act = FS2_ACT_LRELU; c.in_slope = 0.1f; c.alpha = 1.f;
+      c.in_act = FS2_ACT_LRELU; c.in_slope = 0.1f; c.alpha = 1.f; c.tc_variant = tcv;
       c.y = bu + (size_t)g * (u / 2) * Co; c.y_batch_stride = (int64_t)Ti * u * Co; c.y_row_stride = (int64_t)u * Co;
       FS2_TRY(conv1d_dispatch(&c, s));
     }
@@ -306,11 +314,11 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
       for (int d = 0; d < m->n_dil; d++) {
         const int dil = m->rb_dil[j][d];
         FS2_TRY(conv(s, r, B, Ti, C, m->w_rb1[rb][d], m->w_rb1_tc[rb][d], m->b_rb1[rb][d], C, k, dil, (k * dil - dil) / 2, FS2_ACT_LRELU,
-                     0.1f, bt, nullptr, FS2_ACT_LRELU, 0.1f));
+                     0.1f, bt, nullptr, FS2_ACT_LRELU, 0.1f, 1.f, 0, nullptr, tcv));
         const bool last = d == m->n_dil - 1;
         float* dst = last ? bx : (r == r1 ? r2 : r1);
         FS2_TRY(conv(s, bt, B, Ti, C, m->w_rb2[rb][d], m->w_rb2_tc[rb][d], m->b_rb2[rb][d], C, k, 1, (k - 1) / 2, FS2_ACT_NONE, 0.f, dst,
-                     r, FS2_ACT_NONE, 0.f, last ? inv_nk : 1.f, last && j > 0));
+                     r, FS2_ACT_NONE, 0.f, last ? inv_nk : 1.f, last && j > 0, nullptr, tcv));
         r = dst;
       }
     }
@@ -327,7 +335,7 @@ using namespace fs2;
 
 extern "C" {
 
-int fs2_abi_version(void) { return 4; }
+int fs2_abi_version(void) { return 5; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
 int fs2_conv_tc_plan(const fs2_conv1d_args* a, int num_sms, int32_t* out) { return conv_tc_plan_query(a, num_sms, out); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count.load(); }

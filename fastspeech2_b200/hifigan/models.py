@@ -33,6 +33,10 @@ class Generator(nn.Module):
         self.num_upsamples = len(self._hd["upsample_rates"])
         self._weight_norm = True
         self.use_tensor_cores = True     # split-FP16 tcgen05 kernel for every conv it supports; False = fp32 CUDA-core kernels only
+        # Operand split per part (bit 0 = conv_pre, bit 1+i = upsample stage i): set = fp16 main term + one E4M3 correction MMA
+        # (2/3 of the tensor time, waveform error ~3e-5 of the 1e-4 bar when used everywhere), clear = three fp16 MMAs (~2e-6).
+        # Default: the two wide, tensor-bound stages (256 / 128 channels, 64 % of the FLOPs); scripts/emul_split_precision.py.
+        self.f8_mask = 0b00110
         populate(self, hifigan_spec(self._hd, weight_norm=True))
         with torch.no_grad():  # g = ||v|| so that the initial folded weight equals v, as torch's weight_norm does
             for base in self._bases():
@@ -106,8 +110,9 @@ class Generator(nn.Module):
             if k != 2 * u or u % 2:
                 raise L.Fs2Error("ConvTranspose1d stage needs kernel = 2*stride and even stride on the sm_100a path")
             m.rates[i], m.up_k[i] = u, k
+        m.f8_mask = int(self.f8_mask) if self.use_tensor_cores else 0
         pk = packing.pack_vocoder(lambda b: self._folded(b).float(), lambda b: get(self, b + ".bias").detach().float(),
-                                  hd["upsample_rates"], m.n_stages * m.n_kernels, m.n_dil)
+                                  hd["upsample_rates"], m.n_stages * m.n_kernels, m.n_dil, f8_mask=m.f8_mask)
         P = lambda k: pk[k].data_ptr()
         m.w_pre, m.b_pre, m.w_post, m.b_post = P("w_pre"), P("b_pre"), P("w_post"), P("b_post")
         T = lambda k: pk[k + "_tc"].data_ptr() if (self.use_tensor_cores and k + "_tc" in pk) else 0

@@ -51,7 +51,8 @@ class FastSpeech2(nn.Module):
         self.max_seq_len = int(model_config["max_seq_len"])
         # Which sub-networks may run on the split-FP16 tcgen05 kernel.  Encoder and predictors stay on the exact fp32 kernels:
         # they feed the discrete duration / pitch-bucket decisions (hard part 2) and are <1% of the FLOPs.
-        self.tc_mask = L.TC_DECODER | L.TC_POSTNET
+        # *_F8: those parts use the two-MMA operand split (fp16 main term + E4M3 correction, include/fs2b200.h FS2_TC_VARIANT_F8).
+        self.tc_mask = L.TC_DECODER | L.TC_POSTNET | L.TC_DECODER_F8 | L.TC_POSTNET_F8
         self._packed = None          # (AcousticModel struct, keep-alive tensors, device)
         self._pos_long = {}          # device position tables longer than max_seq_len, keyed by width
         self._ws = None
@@ -89,7 +90,8 @@ class FastSpeech2(nn.Module):
         while f"postnet.convolutions.{n_post}.0.conv.weight" in self._keys():
             n_post += 1
         pk = packing.pack_acoustic(lambda k: get(self, k).detach().float(), tr["encoder_layer"], tr["decoder_layer"], n_post,
-                                   self.multi_speaker)
+                                   self.multi_speaker, f8_decoder=bool(self.tc_mask & L.TC_DECODER_F8),
+                                   f8_postnet=bool(self.tc_mask & L.TC_POSTNET_F8))
         m = L.AcousticModel()
         m.d_model, m.n_head, m.d_inner = tr["encoder_hidden"], tr["encoder_head"], tr["conv_filter_size"]
         m.k1, m.k2 = tr["conv_kernel_size"]

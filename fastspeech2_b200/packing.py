@@ -50,31 +50,57 @@ def split_fp16(w: Tensor):
     return hi, lo, s
 
 
-def pack_conv_tc(w: Tensor):
+F8_W_HI_SCALE = 2.0 ** -12      # weight hi -> E4M3 (pairs with the kernel's activation-lo scale 2^12, conv_tc_kernel.cuh)
+F8_W_LO_SCALE = 2.0 ** -1       # weight lo -> E4M3 (pairs with the activation-hi scale 2)
+
+
+def _e4m3_bytes(x: Tensor) -> Tensor:
+    """fp32 -> E4M3 (round to nearest, saturating at +-448) as uint8."""
+    return x.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def pack_conv_tc(w: Tensor, f8: bool = False):
     """[taps][Cin][N] fp32 -> byte buffer for the tcgen05 kernel (see include/fs2b200.h):
-         128-byte header (float32[0] = 1/scale)  |  [N/NB][Cin/16][taps][hi|lo][2 K-chunks][NB][8 halfs]
-    Every (tap, 16-channel K-block) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major, fp16).
+         128-byte header (float32[0] = 1/scale, int32[1] = format)  |  [N/NB][Cin/16][taps][2 planes][2 K-chunks][NB][16 bytes]
+    Every (tap, 16-channel K-block) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major).
+      f8 = False (format 0): plane 0 = fp16 hi, plane 1 = fp16 lo; a chunk row holds 8 channels.
+      f8 = True  (format 1, FS2_TC_VARIANT_F8): plane 0 = fp16 hi; plane 1 = E4M3 with chunk 0 = hi * 2^-12 and chunk 1 = lo * 2^-1 of the
+        K-block's 16 channels -- the B operand of one K = 32 kind::f8f6f4 MMA against the activations' [lo * 2^12 | hi * 2].
     Returns None when the shape is not served by the tensor-core kernel."""
     taps, cin, n = w.shape
     nb = conv_tc_block(n)
     if nb == 0 or cin % 16:
         return None
     hi, lo, s = split_fp16(w)
-    both = torch.stack([hi, lo], dim=0)                                  # [2][taps][Cin][N]
-    t = both.reshape(2, taps, cin // 16, 2, 8, n // nb, nb)              # [2][tap][kb][chunk][e][nblk][nn]
-    tiles = t.permute(5, 2, 1, 0, 3, 6, 4).contiguous()                  # [nblk][kb][tap][2][chunk][nn][e]
+    kb, nblk = cin // 16, n // nb
+    hi_t = hi.reshape(taps, kb, 2, 8, nblk, nb).permute(4, 1, 0, 2, 5, 3).contiguous()          # [nblk][kb][tap][chunk][nn][8 halfs]
+    plane0 = hi_t.view(torch.uint8).reshape(nblk, kb, taps, 1, 2 * nb * 16)
+    if f8:
+        ws = w.float() * s
+        lo32 = ws - hi.float()                                                                   # exact remainder (not re-rounded to fp16)
+        h8 = _e4m3_bytes(hi.float() * F8_W_HI_SCALE).reshape(taps, kb, 16, nblk, nb).permute(3, 1, 0, 4, 2)   # [nblk][kb][tap][nn][16]
+        l8 = _e4m3_bytes(lo32 * F8_W_LO_SCALE).reshape(taps, kb, 16, nblk, nb).permute(3, 1, 0, 4, 2)
+        plane1 = torch.stack([h8, l8], dim=3).contiguous().reshape(nblk, kb, taps, 1, 2 * nb * 16)
+    else:
+        lo_t = lo.reshape(taps, kb, 2, 8, nblk, nb).permute(4, 1, 0, 2, 5, 3).contiguous()
+        plane1 = lo_t.view(torch.uint8).reshape(nblk, kb, taps, 1, 2 * nb * 16)
+    tiles = torch.cat([plane0, plane1], dim=3).contiguous()
     header = torch.zeros(TC_HEADER_BYTES // 4, dtype=torch.float32, device=w.device)
     header[0] = 1.0 / s
-    return torch.cat([header.view(torch.uint8), tiles.view(torch.uint8).reshape(-1)])
+    hb = header.view(torch.uint8).clone()
+    hb[4] = 1 if f8 else 0
+    return torch.cat([hb, tiles.reshape(-1)])
 
 
-def add_tc_tiles(pk: Dict[str, Tensor], keys) -> None:
-    """For every packed conv weight key in `keys` add '<key>_tc' when the tensor-core kernel can take it."""
+def add_tc_tiles(pk: Dict[str, Tensor], keys, f8_keys=()) -> None:
+    """For every packed conv weight key in `keys` add '<key>_tc' when the tensor-core kernel can take it; keys also listed in
+    `f8_keys` get the f16 + f8 operand format."""
+    f8_keys = set(f8_keys)
     for k in keys:
         w = pk[k]
         if w.dim() == 2:
             w = w[None]
-        t = pack_conv_tc(w)
+        t = pack_conv_tc(w, f8=k in f8_keys)
         if t is not None:
             pk[k + "_tc"] = t
 
@@ -111,7 +137,8 @@ def fold_batchnorm(w: Tensor, b: Tensor, gamma: Tensor, beta: Tensor, mean: Tens
     return wf, bf
 
 
-def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet: int, multi_speaker: bool) -> Dict[str, Tensor]:
+def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet: int, multi_speaker: bool,
+                  f8_decoder: bool = False, f8_postnet: bool = False) -> Dict[str, Tensor]:
     pk: Dict[str, Tensor] = {
         "word_emb": g("encoder.src_word_emb.weight").contiguous(),
         "enc_pos": g("encoder.position_enc")[0].contiguous(),
@@ -140,7 +167,9 @@ def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet:
                                 g(p + ".1.running_mean"), g(p + ".1.running_var"))
         pk[f"post.{i}.w"], pk[f"post.{i}.b"] = conv_w(wf), bf.contiguous()
     tc_keys = [f"{side}.{i}.{w}" for side, n in (("enc", n_enc), ("dec", n_dec)) for i in range(n) for w in ("w_qkv", "w_o", "w_1", "w_2")]
-    add_tc_tiles(pk, tc_keys + ["w_mel"] + [f"post.{i}.w" for i in range(n_postnet)])
+    post_keys = ["w_mel"] + [f"post.{i}.w" for i in range(n_postnet)]
+    f8 = ([k for k in tc_keys if k.startswith("dec.")] if f8_decoder else []) + (post_keys if f8_postnet else [])
+    add_tc_tiles(pk, tc_keys + post_keys, f8)
     return pk
 
 
@@ -174,8 +203,10 @@ def split_conv_transpose(w: Tensor, u: int):
     return wa.contiguous(), wb.contiguous()
 
 
-def pack_vocoder(w_of: Callable[[str], Tensor], b_of: Callable[[str], Tensor], rates, n_resblocks: int, n_dil: int) -> Dict[str, Tensor]:
-    """`w_of(base)` returns the folded weight of conv `base`, `b_of(base)` its bias."""
+def pack_vocoder(w_of: Callable[[str], Tensor], b_of: Callable[[str], Tensor], rates, n_resblocks: int, n_dil: int,
+                 f8_mask: int = 0) -> Dict[str, Tensor]:
+    """`w_of(base)` returns the folded weight of conv `base`, `b_of(base)` its bias.  f8_mask: bit 0 = conv_pre, bit 1+i = every conv of
+    upsample stage i uses the f16 + f8 operand format (fs2_vocoder_model.f8_mask)."""
     pk: Dict[str, Tensor] = {"w_pre": conv_w(w_of("conv_pre")), "b_pre": b_of("conv_pre").contiguous()}
     for i, u in enumerate(rates):
         wa, wb = split_conv_transpose(w_of(f"ups.{i}"), u)
@@ -189,6 +220,14 @@ def pack_vocoder(w_of: Callable[[str], Tensor], b_of: Callable[[str], Tensor], r
             pk[f"rb.{rb}.{d}.b2"] = b_of(f"resblocks.{rb}.convs2.{d}").contiguous()
     pk["w_post"] = w_of("conv_post")[0].t().contiguous()      # [1, C, 7] -> [7][C]
     pk["b_post"] = b_of("conv_post").contiguous()
-    add_tc_tiles(pk, ["w_pre"] + [f"up.{i}.{g}" for i in range(len(rates)) for g in ("wa", "wb")]
-                 + [f"rb.{rb}.{d}.{w}" for rb in range(n_resblocks) for d in range(n_dil) for w in ("w1", "w2")])
+    nk = n_resblocks // len(rates)
+    keys = ["w_pre"] + [f"up.{i}.{g}" for i in range(len(rates)) for g in ("wa", "wb")] \
+        + [f"rb.{rb}.{d}.{w}" for rb in range(n_resblocks) for d in range(n_dil) for w in ("w1", "w2")]
+
+    def stage_of(k):
+        if k == "w_pre":
+            return -1
+        idx = int(k.split(".")[1])
+        return idx if k.startswith("up.") else idx // nk
+    add_tc_tiles(pk, keys, [k for k in keys if f8_mask & (1 << (stage_of(k) + 1))])
     return pk

@@ -75,6 +75,12 @@ def fastspeech2_state_dict(preprocess_config, model_config, seed: int = 0,
     stats, _ = read_dataset_files(preprocess_config)
     g = torch.Generator().manual_seed(1000 + seed)
     sd = {p.key: _draw(p, g, stats) for p in fastspeech2_spec(preprocess_config, model_config)}
+    ve = model_config["variance_embedding"]
+    for name in ("pitch", "energy"):                   # log-spaced edges exactly as the reference builds them (model/modules.py:48-54,:60-67)
+        if ve[f"{name}_quantization"] == "log":
+            import numpy as np
+            sd[f"variance_adaptor.{name}_bins"] = torch.exp(
+                torch.linspace(np.log(stats[name][0]), np.log(stats[name][1]), ve["n_bins"] - 1))
     if frames_per_phoneme is not None:
         sd["variance_adaptor.duration_predictor.linear_layer.weight"] *= 0.05
         sd["variance_adaptor.duration_predictor.linear_layer.bias"].fill_(math.log(frames_per_phoneme + 1.0))

@@ -44,7 +44,14 @@ enum {
 enum { FS2_ACT_NONE = 0, FS2_ACT_RELU = 1, FS2_ACT_TANH = 2, FS2_ACT_LRELU = 3 };
 enum { FS2_CONV_AUTO = 0, FS2_CONV_SIMT = 1, FS2_CONV_TC = 2 };
 /* which parts of the acoustic model may use the split-FP16 tcgen05 kernel (fs2_acoustic_model.tc_mask) */
-enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POSTNET = 8 };
+enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POSTNET = 8,
+       /* the decoder's / PostNet's w_*_tc tiles are in the f16+f8 format (see FS2_TC_VARIANT_F8) */
+       FS2_TC_DECODER_F8 = 16, FS2_TC_POSTNET_F8 = 32 };
+/* fs2_conv1d_args.tc_variant bits.  F8: w_tc holds the two-MMA operand split -- fp16 hi tiles as in the three-MMA split, and in
+ * place of the fp16 lo tiles E4M3 tiles [hi * 2^-12 | lo * 2^-1] that one K = 32 kind::f8f6f4 MMA multiplies with the activations'
+ * [lo * 2^12 | hi * 2]: y ~ a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo) with the bracket at E4M3 precision (relative error ~2^-16 instead
+ * of ~2^-22; 2/3 of the tensor-pipe time and shared-memory operand traffic).  Activations beyond +-224 saturate in the correction. */
+enum { FS2_TC_VARIANT_F8 = 1 };
 
 /* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per work item,
  * s = a per-layer power of two, hi = fp16(s*w), lo = fp16(s*w - hi), the tiled byte buffer is
@@ -83,7 +90,7 @@ typedef struct fs2_conv1d_args {
   int N, taps, dilation, pad_left;
   const float* w_tc; /* NULL, or the same weights in the tcgen05 tile layout (see "tensor-core weight tiles" below) */
   int backend;       /* FS2_CONV_AUTO: split-FP16 tcgen05 kernel when w_tc is given and the shape qualifies, else the fp32 CUDA-core kernel */
-  unsigned tc_variant; /* 0; reserved (A/B experiments) */
+  unsigned tc_variant; /* FS2_TC_VARIANT_* bits describing the format of w_tc */
   int in_act; float in_slope;
   int out_act; float out_slope;
   const float* res; int64_t res_batch_stride, res_row_stride; /* NULL = none */
@@ -251,6 +258,7 @@ typedef struct fs2_vocoder_model {
   /* tensor-core tiles (NULL = CUDA-core kernel for that conv) */
   const float *w_pre_tc, *w_up_a_tc[FS2_MAX_STAGES], *w_up_b_tc[FS2_MAX_STAGES];
   const float *w_rb1_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *w_rb2_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL];
+  int f8_mask; /* bit 0: w_pre_tc, bit 1+i: every *_tc tile of stage i is in the f16+f8 format (FS2_TC_VARIANT_F8) */
 } fs2_vocoder_model;
 
 typedef struct fs2_vocoder_args {

@@ -35,6 +35,12 @@ def conv1d(x, w, bias, dilation=1, pad_left=0, in_act=ACT_NONE, in_slope=0.0, ou
         lo, hi = max(0, -shift), min(T, T - shift)
         if hi > lo:
             acc[:, lo:hi] += xa[:, lo + shift:hi + shift] @ w[j]
+    return conv1d_epilogue(acc, bias, out_act, out_slope, res, alpha, y_prev, row_lens)
+
+
+def conv1d_epilogue(acc, bias, out_act=ACT_NONE, out_slope=0.0, res=None, alpha=1.0, y_prev=None, row_lens=None):
+    """Everything fs2_conv1d does after the tap / channel sums (bias, activation, residual, alpha, accumulate, pad-row mask)."""
+    T = acc.shape[1]
     if bias is not None:
         acc = acc + bias
     v = _act(acc, out_act, out_slope)

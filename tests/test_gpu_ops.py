@@ -93,6 +93,50 @@ def test_conv1d_tensor_core(case):
     assert err < 6e-5, err
 
 
+def _f8_operand_emulation(x, w, in_act, in_slope):
+    """The operands the f16 + f8 kernel multiplies, evaluated exactly: returns (a_hi, w_hi, a_lo8, w_hi8, a_hi8, w_lo8, scale) in fp64
+    so that  y*scale = a_hi.w_hi + a_lo8.w_hi8 + a_hi8.w_lo8  (conv_tc_kernel.cuh::tc_convert_store, packing.pack_conv_tc)."""
+    e4 = lambda t: t.float().clamp(-448, 448).to(torch.float8_e4m3fn).double()
+    a = x.float()
+    if in_act == 3:
+        a = torch.maximum(a, a * in_slope)
+    ah = a.half().float()
+    al = a - ah
+    hi, _, s = packing.split_fp16(w)
+    wl = w.float() * s - hi.float()
+    return (ah.double(), hi.double(), e4(al * 4096.0) / 4096.0, e4(hi.float() * 2.0 ** -12) * 4096.0, e4(ah * 2.0) / 2.0, e4(wl * 0.5) * 2.0, s)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv1d_tensor_core_f8_split(case):
+    """FS2_TC_VARIANT_F8 (fp16 main term + one E4M3 correction MMA): (a) the kernel computes exactly the rounded-operand products of
+    its contract (checked against an fp64 evaluation of those operands, so a wrong byte order / scale / K layout cannot hide),
+    (b) against the unrounded fp64 contract the error is at the 2^-16 level (budget for the parity bars: scripts/emul_split_precision.py)."""
+    B, T, Cin, N, taps, dil, pad, in_act, out_act, use_res, alpha, acc, use_lens = case
+    x = rnd(B, T, Cin, seed=1)
+    w = rnd(taps, Cin, N, seed=2, scale=(taps * Cin) ** -0.5)
+    bias = rnd(N, seed=3, scale=0.1)
+    res = rnd(B, T, N, seed=4) if use_res else None
+    y0 = rnd(B, T, N, seed=5) if acc else None
+    lens = torch.tensor([max(1, T - 7 * (i + 1)) for i in range(B)], dtype=torch.int32) if use_lens else None
+    d = lambda t: None if t is None else t.double()
+    exact = E.conv1d(x.double(), w.double(), bias.double(), dil, pad, in_act, 0.1, out_act, 0.1, d(res), alpha, d(y0), lens)
+    ah, wh, al8, wh8, ah8, wl8, s = _f8_operand_emulation(x, w, in_act, 0.1)
+    lin = lambda a_, w_: E.conv1d(a_, w_, None, dil, pad, 0, 0.0, 0, 0.0, None, 1.0, None, None)
+    pre = (lin(ah, wh) + lin(al8, wh8) + lin(ah8, wl8)) / s                       # pre-activation, no bias
+    want = E.conv1d_epilogue(pre, bias.double(), out_act, 0.1, d(res), alpha, d(y0), lens)
+    wtc = packing.pack_conv_tc(w, f8=True)
+    out = y0.to(DEV).clone() if acc else None
+    got = ops.conv1d(x.to(DEV), w.to(DEV), bias.to(DEV), dilation=dil, pad_left=pad, in_act=in_act, in_slope=0.1, out_act=out_act,
+                     out_slope=0.1, res=None if res is None else res.to(DEV), alpha=alpha, out=out, accumulate=acc,
+                     row_lens=None if lens is None else lens.to(DEV), w_tc=wtc.to(DEV), backend=2, tc_variant=1)
+    torch.cuda.synchronize()
+    err_contract = (got.cpu().double() - want).abs().max().item()
+    err_exact = (got.cpu().double() - exact).abs().max().item()
+    assert err_contract < 6e-5, (err_contract, err_exact)      # same budget as the three-MMA split: only the accumulator's rounding
+    assert err_exact < 1.5e-3, (err_contract, err_exact)       # ~2^-16 relative on O(1..10) outputs (single-pass fp16: ~2e-2 here)
+
+
 def test_conv1d_tensor_core_alignment_contract():
     """The tcgen05 kernel reads activations with 256-bit loads: a 16-byte-but-not-32-byte aligned x is refused by the explicit
     backend and silently served by the exact fp32 kernel under FS2_CONV_AUTO (same contract, fp32 accuracy)."""

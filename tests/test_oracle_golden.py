@@ -36,6 +36,40 @@ def test_acoustic_oracle_reproduces_reference_outputs(name, ds, scratch):
     assert (out64[1].float() - t("postnet_mel")).abs().max() < 2e-5
 
 
+def test_acoustic_oracle_reproduces_reference_outputs_paper_config(scratch):
+    """config/LJSpeech_paper: 4-layer decoder, frame-level pitch / energy, log-spaced pitch edges (model/modules.py:48-54,:139-148)."""
+    from oracle.gen_golden import paper_state_dict
+    z = np.load(os.path.join(GOLD, "fs2_lj_paper.npz"))
+    pc, mc = configs.make_configs("LJSpeech_paper", scratch)
+    sd = paper_state_dict(pc, mc, int(z["seed"]))
+    assert sum(k.endswith("slf_attn.fc.bias") for k in sd if k.startswith("decoder.")) == 4
+    edges = sd["variance_adaptor.pitch_bins"]
+    assert not torch.allclose(edges[1:] - edges[:-1], (edges[1] - edges[0]).expand(edges.numel() - 1))     # log-spaced
+    t = lambda k: torch.from_numpy(z[k])
+    out = O.fastspeech2_forward(sd, t("speakers"), t("texts"), t("src_lens"), int(z["max_src_len"]), p_control=float(z["p_control"]),
+                                pitch_level="frame_level", energy_level="frame_level")
+    assert torch.equal(out[5], t("d_rounded")) and torch.equal(out[9], t("mel_lens")) and torch.equal(out[7], t("mel_masks"))
+    assert out[2].shape == t("p_pred").shape == out[0].shape[:2]
+    for i, k in ((0, "mel"), (1, "postnet_mel"), (4, "logd")):
+        assert (out[i] - t(k)).abs().max() < 5e-6, k
+    for i, k in ((2, "p_pred"), (3, "e_pred")):     # raw-valued (hundreds; head weights x100..250 amplify the thread-count noise): relative
+        assert ((out[i] - t(k)).abs() / (1 + t(k).abs())).max() < 5e-5, k
+
+
+@pytest.mark.parametrize("name", ["LJSpeech", "universal"])
+def test_vocoder_oracle_reproduces_reference_outputs_real_checkpoint(name):
+    """The shipped generator weights (hifigan/generator_*.pth.tar.zip): oracle vs the unmodified reference's committed output."""
+    from oracle import real_ckpt
+    sd = real_ckpt.load(name)
+    if sd is None and os.path.exists(real_ckpt.source_zip(name)):
+        sd = real_ckpt.read_reference_checkpoint(name)
+    if sd is None:
+        pytest.skip("real checkpoint fixture not present (run __graft_entry__.build() where /root/reference exists)")
+    z = np.load(os.path.join(GOLD, f"hifigan_real_{name}.npz"))
+    wav = O.hifigan_forward(sd, torch.from_numpy(z["mel"]))
+    assert (wav - torch.from_numpy(z["wav"])).abs().max() < 2e-6
+
+
 def test_vocoder_oracle_reproduces_reference_outputs():
     z = np.load(os.path.join(GOLD, "hifigan.npz"))
     sd = synth.hifigan_state_dict(configs.HIFIGAN_CONFIG, seed=int(z["seed"]))
@@ -49,7 +83,7 @@ def test_state_dict_key_contract(scratch):
     from fastspeech2_b200.hifigan import AttrDict, Generator
     from fastspeech2_b200.model import FastSpeech2
     want = json.load(open(os.path.join(GOLD, "state_dict_keys.json")))
-    for ds in ("LJSpeech", "LibriTTS"):
+    for ds in ("LJSpeech", "LibriTTS", "LJSpeech_paper"):
         pc, mc = configs.make_configs(ds, scratch)
         got = {k: list(v.shape) for k, v in FastSpeech2(pc, mc).state_dict().items()}
         assert got == want[ds]
