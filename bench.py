@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2, help="utterances in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--voc-f8-mask", type=int, default=None, help="override hifigan.Generator.f8_mask (A/B of the operand split)")
+    ap.add_argument("--voc-fused-mask", type=int, default=None, help="override hifigan.Generator.fused_mask (A/B of the fused ResBlock-group kernel)")
     ap.add_argument("--fs2-f8", type=int, default=None, choices=[0, 1], help="override the decoder / PostNet operand split (A/B)")
     return ap.parse_args()
 
@@ -206,6 +207,8 @@ def run_ours(args):
     voc.load_state_dict(synth.hifigan_state_dict(configs.HIFIGAN_CONFIG, seed=0))
     if args.voc_f8_mask is not None:
         voc.f8_mask = args.voc_f8_mask
+    if args.voc_fused_mask is not None:
+        voc.fused_mask = args.voc_fused_mask
     voc.eval()
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -341,7 +344,7 @@ def run_ours(args):
                           "fastspeech2_only_mel_frames_per_s": mel_fps, "fastspeech2_only_ms_per_step": ms_mel / args.steps,
                           "algorithmic_tflop_per_step": (FS2_FLOPS(args.phonemes, frames_step / (args.batch * world)) * args.batch * world
                                                          + HIFIGAN_FLOPS_PER_FRAME * frames_step) / 1e12,
-                          "operand_split": {"vocoder_f8_mask": int(voc.f8_mask), "fs2_tc_mask": int(model.tc_mask)},
+                          "operand_split": {"vocoder_f8_mask": int(voc.f8_mask), "vocoder_fused_stage_mask": int(voc.fused_mask), "fs2_tc_mask": int(model.tc_mask)},
                           "build": lib.fs2_build_info().decode()}}
         print(json.dumps(line), flush=True)
     if world > 1:

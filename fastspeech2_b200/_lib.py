@@ -127,7 +127,15 @@ class VocoderModel(C.Structure):
                 ("w_post", fp), ("b_post", fp),
                 ("w_pre_tc", fp), ("w_up_a_tc", fp * MAX_STAGES), ("w_up_b_tc", fp * MAX_STAGES),
                 ("w_rb1_tc", (fp * MAX_DIL) * MAX_RESBLOCKS), ("w_rb2_tc", (fp * MAX_DIL) * MAX_RESBLOCKS),
-                ("f8_mask", i32)]
+                ("f8_mask", i32), ("fused_mask", i32)]
+
+
+class ResstackArgs(C.Structure):
+    _K = MAX_DIL + 4
+    _fields_ = [("x", fp), ("y", fp), ("B", i32), ("N", i32), ("C", i32), ("n_kernels", i32), ("n_dil", i32),
+                ("k", i32 * (MAX_DIL + 4)), ("dil", (i32 * MAX_DIL) * (MAX_DIL + 4)),
+                ("w1_tc", (fp * MAX_DIL) * (MAX_DIL + 4)), ("b1", (fp * MAX_DIL) * (MAX_DIL + 4)),
+                ("w2_tc", (fp * MAX_DIL) * (MAX_DIL + 4)), ("b2", (fp * MAX_DIL) * (MAX_DIL + 4))]
 
 
 class VocoderArgs(C.Structure):
@@ -155,6 +163,8 @@ EXPORTS = {
     "fs2_durations": (i32, [C.POINTER(DurationsArgs), fp]),
     "fs2_length_regulate": (i32, [C.POINTER(LengthRegulateArgs), fp]),
     "fs2_conv_post": (i32, [C.POINTER(ConvPostArgs), fp]),
+    "fs2_resstack": (i32, [C.POINTER(ResstackArgs), fp]),
+    "fs2_resstack_plan": (i32, [C.POINTER(ResstackArgs), i32, C.c_void_p]),
     "fs2_transpose_bct_to_btc": (i32, [fp, fp, i32, i32, i32, fp]),
     "fs2_add_positions": (i32, [fp, fp, i32, i32, i32, fp]),
     "fs2_encode_workspace_bytes": (C.c_size_t, [C.POINTER(AcousticModel), i32, i32]),

@@ -1,7 +1,8 @@
 """Compile the CUDA sources under csrc/ into fastspeech2_b200/libfs2b200.so for sm_100a (in-tree, so it ships with gpurun).
 
 Each .cu is compiled to an object in parallel (build/obj/, git-ignored) and the objects are linked with nvcc --shared.
-FS2_TC_TRACE=1 in the environment compiles the per-role timeline stamps into the tcgen05 conv kernel (scripts/tc_trace.py).
+FS2_TC_TRACE=1 in the environment compiles the per-role timeline stamps into the tcgen05 conv kernel (scripts/tc_trace.py);
+FS2_DEBUG_KNOBS=1 compiles the fs2_debug_set_* tuning knobs that scripts/tc_*.py use (the shipped library has neither).
 """
 from __future__ import annotations
 
@@ -17,7 +18,8 @@ LIB = os.path.join(HERE, "libfs2b200.so")
 OBJ = os.path.join(ROOT, "build", "obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-I", os.path.join(ROOT, "include")] + (["-DFS2_TC_TRACE"] if os.environ.get("FS2_TC_TRACE") == "1" else [])
+         "-I", os.path.join(ROOT, "include")] + (["-DFS2_TC_TRACE", "-DFS2_DEBUG_KNOBS"] if os.environ.get("FS2_TC_TRACE") == "1" else []) \
+        + (["-DFS2_DEBUG_KNOBS"] if os.environ.get("FS2_DEBUG_KNOBS") == "1" and os.environ.get("FS2_TC_TRACE") != "1" else [])
 
 
 def sources():

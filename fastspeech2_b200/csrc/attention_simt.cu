@@ -172,11 +172,16 @@ int attention_simt(const fs2_attention_args* a, cudaStream_t s) {
   if (!a || !a->qkv || !a->ctx || a->B <= 0 || a->T <= 0 || a->H <= 0) return FS2_ERR_ARG;
   if (a->Dh != ATT_D) return FS2_ERR_UNSUPPORTED;
   if (!aligned16(a->qkv) || !aligned16(a->ctx)) return FS2_ERR_ARG;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
-    if (e != cudaSuccess) return FS2_ERR_CUDA - (int)e;
-    attr_set = true;
+  int derr = FS2_OK;
+  DevState* dv = dev_state(&derr);
+  if (!dv) return derr;
+  if (!dv->att_simt_ready.load(std::memory_order_acquire)) {
+    DevOnce once;
+    if (!dv->att_simt_ready.load(std::memory_order_relaxed)) {
+      cudaError_t e = cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
+      if (e != cudaSuccess) return FS2_ERR_CUDA - (int)e;
+      dv->att_simt_ready.store(true, std::memory_order_release);
+    }
   }
   dim3 grid((a->T + ATT_BQ - 1) / ATT_BQ, a->H, a->B);
   prof_before(s);

@@ -29,8 +29,22 @@ inline int cuda_status() {
     if (_st != FS2_OK) return _st;         \
   } while (0)
 
-// optional per-launch event timing (see fs2_profile_begin in fs2b200.h)
-extern bool g_prof_on;
+// Per-device one-time setup (SM count, >48 KB dynamic shared memory opt-ins).  cudaFuncSetAttribute applies to the CURRENT device's
+// context, so the "done" flags are kept per device ordinal; dev_state() looks the current device up (thread-safe) and
+// DevOnce serialises the first call per (device, kernel family).
+constexpr int FS2_MAX_DEVICES = 64;
+struct DevState {
+  std::atomic<int> num_sms{0};
+  std::atomic<bool> conv_tc_ready{false}, att_simt_ready{false}, fused_ready{false};
+};
+DevState* dev_state(int* err);                       // NULL + *err on failure
+struct DevOnce {                                     // RAII lock around a first-use setup section
+  DevOnce();
+  ~DevOnce();
+};
+
+// optional per-launch event timing (see fs2_profile_begin in fs2b200.h); armed per host thread
+extern thread_local bool g_prof_on;
 void prof_before(cudaStream_t s);
 void prof_after(cudaStream_t s, int cls, double flops);
 

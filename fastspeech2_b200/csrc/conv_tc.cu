@@ -5,7 +5,11 @@
 namespace fs2 {
 
 // ------------------------------------------------------------------ host side
+#ifdef FS2_DEBUG_KNOBS
 long long* g_tc_trace = nullptr;  // debug: set through fs2_debug_set_tc_trace (per-item role timeline)
+#else
+static constexpr long long* g_tc_trace = nullptr;
+#endif
 
 static int pow2_cols(int c) {
   int v = 32;
@@ -33,12 +37,16 @@ bool conv_tc_supported(const fs2_conv1d_args* a) {
   return true;
 }
 
-static int g_num_sms = 0;
+#ifdef FS2_DEBUG_KNOBS
 int g_tc_pdl = 0;                  // programmatic dependent launch: 0 = off (default), 1 = short launches only, 2 = every launch.
                                    // Measured with the three modes interleaved step by step (scripts/pdl_ab.py,
                                    // profiles/r01_pdl_ab.txt): no gain on either forward (39.5 / 40.8 / 42.2 ms per step), so it
                                    // stays off; debug switch fs2_debug_set_tc_pdl
 int g_tc_tune[4] = {0, 0, 0, 0};   // debug overrides: SA, SB, TPS, grid (0 = heuristic); set through fs2_debug_set_tc_tuning
+#else                              // shipped build: no mutable process-wide state
+static constexpr int g_tc_pdl = 0;
+static constexpr int g_tc_tune[4] = {0, 0, 0, 0};
+#endif
 
 // Shape-derived launch plan (pure host logic, no CUDA calls): work-item shape, accumulator grouping, ring depths, shared /
 // tensor memory budget, grid.  Returns FS2_OK or FS2_ERR_UNSUPPORTED.  Exposed as fs2_conv_tc_plan so that the heuristics'
@@ -119,16 +127,21 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
   if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
   if (!aligned16(a->x) || !aligned16(wt) || !aligned16(a->y) || (a->res && !aligned16(a->res))) return FS2_ERR_ARG;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    const int mx = 227 * 1024;
-    if (e == cudaSuccess) e = conv_tc_prepare_mt1(mx);
-    if (e == cudaSuccess) e = conv_tc_prepare_mt2(mx);
-    if (e == cudaSuccess) e = conv_tc_prepare_mt4(mx);
-    if (e != cudaSuccess) { g_num_sms = 0; return FS2_ERR_CUDA - (int)e; }
+  int derr = FS2_OK;
+  DevState* dv = dev_state(&derr);                      // state of the CURRENT device: the caller's stream must belong to it
+  if (!dv) return derr;
+  if (!dv->conv_tc_ready.load(std::memory_order_acquire)) {
+    DevOnce once;
+    if (!dv->conv_tc_ready.load(std::memory_order_relaxed)) {
+      const int mx = 227 * 1024;
+      cudaError_t e = conv_tc_prepare_mt1(mx);
+      if (e == cudaSuccess) e = conv_tc_prepare_mt2(mx);
+      if (e == cudaSuccess) e = conv_tc_prepare_mt4(mx);
+      if (e != cudaSuccess) return FS2_ERR_CUDA - (int)e;
+      dv->conv_tc_ready.store(true, std::memory_order_release);
+    }
   }
+  const int g_num_sms = dv->num_sms.load(std::memory_order_relaxed);
   TcP p{};
   p.x = a->x; p.xbs = a->x_batch_stride; p.xrs = a->x_row_stride;
   p.B = a->B; p.T = a->T; p.Cin = a->Cin;

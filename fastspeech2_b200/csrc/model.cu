@@ -1,5 +1,6 @@
 // Host-side orchestration of the two forward passes and the extern "C" surface declared in include/fs2b200.h.
 // No allocation, no synchronisation: every launch goes to the caller's stream, temporaries come from the caller's workspace.
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -9,11 +10,36 @@ namespace fs2 {
 
 std::atomic<unsigned long long> g_launch_count{0};
 
-// ------------------------------------------------------------------ per-launch profiling (off unless armed)
-bool g_prof_on = false;
+// ------------------------------------------------------------------ per-device setup state
+static DevState g_dev[FS2_MAX_DEVICES];
+static std::mutex g_dev_mutex;
+DevState* dev_state(int* err) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= FS2_MAX_DEVICES) {
+    if (err) *err = e != cudaSuccess ? FS2_ERR_CUDA - (int)e : FS2_ERR_UNSUPPORTED;
+    return nullptr;
+  }
+  DevState* d = &g_dev[dev];
+  if (d->num_sms.load(std::memory_order_acquire) == 0) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || n <= 0) {
+      if (err) *err = FS2_ERR_CUDA - (int)e;
+      return nullptr;
+    }
+    d->num_sms.store(n, std::memory_order_release);
+  }
+  return d;
+}
+DevOnce::DevOnce() { g_dev_mutex.lock(); }
+DevOnce::~DevOnce() { g_dev_mutex.unlock(); }
+
+// ------------------------------------------------------------------ per-launch profiling (off unless armed; state is per host thread)
+thread_local bool g_prof_on = false;
 struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
-static std::vector<ProfRec> g_prof;
-static cudaEvent_t g_prof_pending;
+static thread_local std::vector<ProfRec> g_prof;
+static thread_local cudaEvent_t g_prof_pending;
 void prof_before(cudaStream_t s) {
   if (!g_prof_on) return;
   cudaEventCreate(&g_prof_pending);
@@ -36,9 +62,11 @@ size_t attention_gemm_workspace(int B, int T, int H);
 bool conv_tc_supported(const fs2_conv1d_args* a);
 int conv_tc_nb(int N);
 int conv_tc_plan_query(const fs2_conv1d_args* a, int num_sms, int* out);
+#ifdef FS2_DEBUG_KNOBS
 extern long long* g_tc_trace;
 extern int g_tc_tune[4];
 extern int g_tc_pdl;
+#endif
 
 // backend dispatch of the fs2_conv1d contract
 static int conv1d_dispatch(const fs2_conv1d_args* a, cudaStream_t s) {
@@ -55,6 +83,8 @@ int variance_head(const fs2_variance_head_args* a, cudaStream_t s);
 int durations(const fs2_durations_args* a, cudaStream_t s);
 int length_regulate(const fs2_length_regulate_args* a, cudaStream_t s);
 int conv_post(const fs2_conv_post_args* a, cudaStream_t s);
+int resstack(const fs2_resstack_args* a, cudaStream_t s);
+int resstack_plan(const fs2_resstack_args* a, int num_sms, int* out);
 int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t s);
 int add_positions(float* x, const float* pos, int B, int T, int D, cudaStream_t s);
 
@@ -97,6 +127,12 @@ static int ln(cudaStream_t s, const float* x, float* y, int B, int T, int C, con
 
 struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; void* att_ws; size_t att_bytes; };
 
+// The GEMM attention materialises S [B*H][T][Tk] in fp32 and keeps a score row in registers: it serves 192 <= T <= 4096 with a
+// workspace of at most 8 GB; anything longer / larger runs the exact flash-style kernel, which has no length limit.
+static bool attention_gemm_usable(int B, int T, int H) {
+  return T >= 192 && T <= 4096 && attention_gemm_workspace(B, T, H) <= ((size_t)8 << 30);
+}
+
 // One FFT block in place on bufs.x  (transformer/Layers.py:21-30)
 static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_block_weights& w, const FftBufs& f, int B, int T,
                      const int32_t* lens, bool tc, unsigned tcv) {
@@ -107,7 +143,7 @@ static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_
   fs2_attention_args at{};
   at.qkv = f.qkv; at.ctx = f.ctx; at.B = B; at.T = T; at.H = m->n_head; at.Dh = D / m->n_head; at.key_lens = lens;
   at.scale = 1.0f / sqrtf((float)(D / m->n_head));
-  if (tc && f.att_ws && T >= 192) {                    // tensor-core path: S = QK^T and PV as split-FP16 GEMMs
+  if (tc && f.att_ws && attention_gemm_usable(B, T, m->n_head)) {   // tensor-core path: S = QK^T and PV as split-FP16 GEMMs
     FS2_TRY(attention_gemm(&at, f.att_ws, f.att_bytes, s));
   } else {
     FS2_TRY(attention_simt(&at, s));
@@ -132,7 +168,7 @@ static bool model_ok(const fs2_acoustic_model* m) {
 static FftBufs fft_bufs(Arena& ar, const fs2_acoustic_model* m, size_t rows, int B = 0, int T = 0, bool tc_attention = false) {
   FftBufs f;
   f.att_ws = nullptr; f.att_bytes = 0;
-  if (tc_attention && T >= 192) {
+  if (tc_attention && attention_gemm_usable(B, T, m->n_head)) {
     f.att_bytes = attention_gemm_workspace(B, T, m->n_head);
     f.att_ws = ar.take(f.att_bytes);
   }
@@ -202,7 +238,7 @@ static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cu
   d.mel_lens32 = a->mel_lens32; d.len_stats = a->len_stats;
   FS2_TRY(durations(&d, s));
   if (a->len_stats_host) {
-    ce = cudaMemcpyAsync(a->len_stats_host, a->len_stats, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    ce = cudaMemcpyAsync(a->len_stats_host, a->len_stats, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
     if (ce != cudaSuccess) return FS2_ERR_CUDA - (int)ce;
   }
   return FS2_OK;
@@ -308,6 +344,22 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
     }
     Ti *= u; C = Co;
     // ---- mean of the multi-receptive-field ResBlocks (models.py:154-160, ResBlock.forward :96-103)
+    if ((m->fused_mask >> i) & 1) {                    // one persistent kernel for the whole group: intermediates never leave the SM
+      if (!tcv) return FS2_ERR_ARG;
+      fs2_resstack_args ra{};
+      ra.x = bu; ra.y = bx; ra.B = B; ra.N = Ti; ra.C = C; ra.n_kernels = m->n_kernels; ra.n_dil = m->n_dil;
+      for (int j = 0; j < m->n_kernels; j++) {
+        ra.k[j] = m->rb_k[j];
+        for (int d = 0; d < m->n_dil; d++) {
+          const int rb = i * m->n_kernels + j;
+          ra.dil[j][d] = m->rb_dil[j][d];
+          ra.w1_tc[j][d] = m->w_rb1_tc[rb][d]; ra.b1[j][d] = m->b_rb1[rb][d];
+          ra.w2_tc[j][d] = m->w_rb2_tc[rb][d]; ra.b2[j][d] = m->b_rb2[rb][d];
+        }
+      }
+      FS2_TRY(resstack(&ra, s));
+      continue;
+    }
     for (int j = 0; j < m->n_kernels; j++) {
       const int rb = i * m->n_kernels + j, k = m->rb_k[j];
       const float* r = bu;
@@ -355,13 +407,17 @@ size_t fs2_struct_size(int which) {
     case 11: return sizeof(fs2_decode_args);
     case 12: return sizeof(fs2_vocoder_model);
     case 13: return sizeof(fs2_vocoder_args);
+    case 14: return sizeof(fs2_resstack_args);
     default: return 0;
   }
 }
-/* debug only (not in the public header): per-CTA phase timestamps of the next tcgen05 conv launches */
+#ifdef FS2_DEBUG_KNOBS
+/* tuning / tracing knobs for scripts/tc_*.py -- compiled in only with -DFS2_DEBUG_KNOBS (FS2_DEBUG_KNOBS=1 python -m fastspeech2_b200.build):
+ * the shipped library has no mutable process-wide state behind the ABI */
 void fs2_debug_set_tc_trace(long long* buf) { g_tc_trace = buf; }
 void fs2_debug_set_tc_pdl(int on) { g_tc_pdl = on; }
 void fs2_debug_set_tc_tuning(int sa, int sb, int tps, int grid) { g_tc_tune[0] = sa; g_tc_tune[1] = sb; g_tc_tune[2] = tps; g_tc_tune[3] = grid; }
+#endif
 int fs2_profile_begin(void) {
   g_prof.clear();
   g_prof_on = true;
@@ -399,6 +455,8 @@ int fs2_variance_head(const fs2_variance_head_args* a, fs2_stream_t st) { return
 int fs2_durations(const fs2_durations_args* a, fs2_stream_t st) { return durations(a, S(st)); }
 int fs2_length_regulate(const fs2_length_regulate_args* a, fs2_stream_t st) { return length_regulate(a, S(st)); }
 int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t st) { return conv_post(a, S(st)); }
+int fs2_resstack(const fs2_resstack_args* a, fs2_stream_t st) { return resstack(a, S(st)); }
+int fs2_resstack_plan(const fs2_resstack_args* a, int num_sms, int32_t* out) { return out ? resstack_plan(a, num_sms, out) : FS2_ERR_ARG; }
 int fs2_add_positions(float* x, const float* pos, int B, int T, int D, fs2_stream_t st) { return add_positions(x, pos, B, T, D, S(st)); }
 int fs2_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, fs2_stream_t st) {
   return transpose_bct_to_btc(in, out, B, C, T, S(st));
@@ -442,8 +500,18 @@ int fs2_acoustic_decode(const fs2_acoustic_model* m, const fs2_decode_args* a, f
 }
 
 static bool vocoder_ok(const fs2_vocoder_model* m) {
-  return m && m->n_stages > 0 && m->n_stages <= FS2_MAX_STAGES && m->n_kernels > 0 && m->n_kernels * m->n_stages <= FS2_MAX_RESBLOCKS &&
-         m->n_dil > 0 && m->n_dil <= FS2_MAX_DIL && m->c0 > 0 && m->n_mel > 0;
+  if (!(m && m->n_stages > 0 && m->n_stages <= FS2_MAX_STAGES && m->n_kernels > 0 && m->n_kernels <= FS2_MAX_DIL + 4 &&
+        m->n_kernels * m->n_stages <= FS2_MAX_RESBLOCKS && m->n_dil > 0 && m->n_dil <= FS2_MAX_DIL && m->c0 > 0 && m->n_mel > 0))
+    return false;
+  if (m->c0 % (1 << m->n_stages)) return false;                          // channels halve at every stage
+  for (int i = 0; i < m->n_stages; i++)
+    if (m->rates[i] <= 0 || m->up_k[i] <= 0) return false;
+  for (int j = 0; j < m->n_kernels; j++) {
+    if (m->rb_k[j] <= 0 || !(m->rb_k[j] & 1)) return false;              // odd kernels: symmetric "same" padding (hifigan/models.py:16-17)
+    for (int d = 0; d < m->n_dil; d++)
+      if (m->rb_dil[j][d] <= 0) return false;
+  }
+  return true;
 }
 
 size_t fs2_vocoder_workspace_bytes(const fs2_vocoder_model* m, int B, int T) {

@@ -225,7 +225,11 @@ __global__ void durations_kernel(const fs2_durations_args a) {
         d = fmaxf(rintf(expf(s) - 1.f) * a.d_control, 0.f);
         if (a.d_rounded) a.d_rounded[(long long)b * a.L + l] = d;
       }
-      reps = max((int)fminf(d, 1.0e6f), 0);  // int() truncation toward zero (bounded so a wild exp() cannot overflow int)
+      // int() truncation toward zero.  A NaN / inf / absurd duration (the reference raises on int(inf) or dies allocating) is counted
+      // in len_stats[2] and contributes no frames, so the caller can fail loudly instead of sizing a gigantic output.
+      const bool wild = !(d <= 1.0e6f);
+      if (wild) atomicAdd(a.len_stats + 2, 1);
+      reps = wild ? 0 : max((int)d, 0);
     }
     int v = reps;
 #pragma unroll
@@ -263,7 +267,7 @@ __global__ void durations_kernel(const fs2_durations_args a) {
 
 int durations(const fs2_durations_args* a, cudaStream_t s) {
   if (!a || !a->src || !a->cum || !a->mel_lens || !a->len_stats || a->B <= 0 || a->L <= 0) return FS2_ERR_ARG;
-  cudaError_t e = cudaMemsetAsync(a->len_stats, 0, 2 * sizeof(int), s);
+  cudaError_t e = cudaMemsetAsync(a->len_stats, 0, 3 * sizeof(int), s);
   if (e != cudaSuccess) return FS2_ERR_CUDA - (int)e;
   durations_kernel<<<a->B, 256, 0, s>>>(*a);
   FS2_LAUNCH_CHECK();

@@ -4,6 +4,7 @@
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -37,6 +38,9 @@ class Generator(nn.Module):
         # (2/3 of the tensor time, waveform error ~3e-5 of the 1e-4 bar when used everywhere), clear = three fp16 MMAs (~2e-6).
         # Default: the two wide, tensor-bound stages (256 / 128 channels, 64 % of the FLOPs); scripts/emul_split_precision.py.
         self.f8_mask = 0b00110
+        # Stages (bit i) whose ResBlock group runs as ONE persistent kernel with every intermediate on chip (fs2_resstack: the 64- and
+        # 32-channel stages); those stages use the f16 + f8 operand format regardless of f8_mask.
+        self.fused_mask = 0b1100
         populate(self, hifigan_spec(self._hd, weight_norm=True))
         with torch.no_grad():  # g = ||v|| so that the initial folded weight equals v, as torch's weight_norm does
             for base in self._bases():
@@ -110,7 +114,14 @@ class Generator(nn.Module):
             if k != 2 * u or u % 2:
                 raise L.Fs2Error("ConvTranspose1d stage needs kernel = 2*stride and even stride on the sm_100a path")
             m.rates[i], m.up_k[i] = u, k
-        m.f8_mask = int(self.f8_mask) if self.use_tensor_cores else 0
+        m.fused_mask = 0
+        if self.use_tensor_cores:
+            ch = m.c0
+            for i in range(m.n_stages):
+                ch //= 2
+                if (int(self.fused_mask) >> i) & 1 and ch in (32, 64):
+                    m.fused_mask |= 1 << i
+        m.f8_mask = (int(self.f8_mask) | (m.fused_mask << 1)) if self.use_tensor_cores else 0
         pk = packing.pack_vocoder(lambda b: self._folded(b).float(), lambda b: get(self, b + ".bias").detach().float(),
                                   hd["upsample_rates"], m.n_stages * m.n_kernels, m.n_dil, f8_mask=m.f8_mask)
         P = lambda k: pk[k].data_ptr()
@@ -135,6 +146,11 @@ class Generator(nn.Module):
     @torch.no_grad()
     def forward(self, x):
         """x: mel [B, 80, T] (any strides; the usual caller passes postnet_mel.transpose(1, 2), utils/tools.py:202)."""
+        dev = get(self, "conv_pre.bias").device
+        with (torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()):   # per-device kernel setup: CURRENT device
+            return self._forward(x)
+
+    def _forward(self, x):
         if self.training:
             raise NotImplementedError("B200-native hifigan.Generator is inference-only: call .eval() (utils/model.py:67)")
         lib = L.lib()

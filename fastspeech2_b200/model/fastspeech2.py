@@ -4,6 +4,7 @@ reference (model/fastspeech2.py:13-110); the forward itself is hand-written sm_1
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -158,6 +159,14 @@ class FastSpeech2(nn.Module):
     @torch.no_grad()
     def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
                 p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0, d_control=1.0):
+        # the C ABI sets up per-device kernel attributes for the CURRENT device: make the model's device current
+        dev = get(self, "mel_linear.weight").device
+        with (torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()):
+            return self._forward(speakers, texts, src_lens, max_src_len, mels, mel_lens, max_mel_len, p_targets, e_targets, d_targets,
+                                 p_control, e_control, d_control)
+
+    def _forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
+                 p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0, d_control=1.0):
         if self.training:
             raise NotImplementedError("B200-native FastSpeech2 is inference-only: call .eval() (utils/model.py:32)")
         p_frame = self.pitch_feature_level == "frame_level"
@@ -183,9 +192,9 @@ class FastSpeech2(nn.Module):
         mel_lens32 = torch.empty(B, dtype=torch.int32, device=dev)
         cum = torch.empty(B, Lmax, dtype=torch.int32, device=dev)
         x_adapted = torch.empty(B, Lmax, m.d_model, **f32)
-        stats_dev = torch.empty(2, dtype=torch.int32, device=dev)
+        stats_dev = torch.empty(3, dtype=torch.int32, device=dev)
         if self._stats_host is None:
-            self._stats_host = torch.empty(2, dtype=torch.int32).pin_memory()
+            self._stats_host = torch.zeros(3, dtype=torch.int32).pin_memory()
         tgt = lambda t: None if t is None else t.to(**f32).contiguous()
         p_t, e_t, d_t = tgt(p_targets), tgt(e_targets), tgt(d_targets)
 
@@ -207,12 +216,15 @@ class FastSpeech2(nn.Module):
             # the one unavoidable host sync: the output shape depends on the predicted durations (utils/tools.py:94)
             torch.cuda.current_stream(dev).synchronize()
             T = int(self._stats_host[0])
+            if int(self._stats_host[2]) != 0:
+                raise L.Fs2Error(f"{int(self._stats_host[2])} predicted durations are NaN / inf / > 1e6 frames "
+                                 "(the reference raises on them too, model/modules.py:186)")
         if T <= 0:
             raise L.Fs2Error("all predicted durations are zero: nothing to decode")
-        if mel_lens is not None:
-            mask_lens32 = mel_lens.to(device=dev, dtype=torch.int32).contiguous()
+        if mel_lens is not None and d_targets is not None:
+            mask_lens32 = mel_lens.to(device=dev, dtype=torch.int32).contiguous()   # teacher forcing: the caller's mask (fastspeech2.py:60-64)
         else:
-            mask_lens32 = mel_lens32
+            mask_lens32 = mel_lens32       # free-running: the adaptor rebuilds the mask from the predicted lengths (modules.py:132-137)
 
         m.dec_pos, m.dec_pos_rows = self._position(1, T, m.d_model, dev)
         mel = torch.empty(B, T, m.n_mel, **f32)

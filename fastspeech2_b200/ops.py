@@ -101,7 +101,7 @@ def durations(src, use_target=False, d_control=1.0):
     cum = torch.empty(B, Lm, dtype=torch.int32, device=dev)
     mel_lens = torch.empty(B, dtype=torch.long, device=dev)
     mel_lens32 = torch.empty(B, dtype=torch.int32, device=dev)
-    stats = torch.empty(2, dtype=torch.int32, device=dev)
+    stats = torch.empty(3, dtype=torch.int32, device=dev)
     a = L.DurationsArgs(src=src.data_ptr(), use_target=int(use_target), d_control=d_control, B=B, L=Lm,
                         d_rounded=0 if use_target else d_rounded.data_ptr(), cum=cum.data_ptr(), mel_lens=mel_lens.data_ptr(),
                         mel_lens32=mel_lens32.data_ptr(), len_stats=stats.data_ptr())
@@ -126,6 +126,24 @@ def conv_post(x, w, bias, in_slope=0.01):
                        wav=wav.data_ptr())
     L.check(L.lib().fs2_conv_post(C.byref(a), _stream(x.device)), "fs2_conv_post")
     return wav
+
+
+def resstack(x, kernels, dilations, w1_tc, b1, w2_tc, b2):
+    """Fused multi-receptive-field ResBlock group (fs2_resstack).  x [B,N,C] contiguous; kernels [k_j]; dilations [[d...] per j];
+    w1_tc / w2_tc [j][d]: pack_conv_tc(w, f8=True) tiles; b1 / b2 [j][d]: biases."""
+    _need_cuda(x)
+    B, N, Cc = x.shape
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    a = L.ResstackArgs(x=x.data_ptr(), y=y.data_ptr(), B=B, N=N, C=Cc, n_kernels=len(kernels), n_dil=len(dilations[0]))
+    for j, k in enumerate(kernels):
+        a.k[j] = k
+        for d, dv in enumerate(dilations[j]):
+            a.dil[j][d] = dv
+            a.w1_tc[j][d], a.b1[j][d] = w1_tc[j][d].data_ptr(), b1[j][d].data_ptr()
+            a.w2_tc[j][d], a.b2[j][d] = w2_tc[j][d].data_ptr(), b2[j][d].data_ptr()
+    L.check(L.lib().fs2_resstack(C.byref(a), _stream(x.device)), "fs2_resstack")
+    return y
 
 
 def transpose_bct_to_btc(x):

@@ -142,15 +142,15 @@ typedef struct fs2_variance_head_args {
 int fs2_variance_head(const fs2_variance_head_args* a, fs2_stream_t stream);
 
 /* d = use_target ? src[b,l] : max(rint(exp(src[b,l]) - 1) * d_control, 0); reps = max((int)d, 0);
- * cum[b,l] = inclusive prefix sum of reps; mel_lens[b] = cum[b,L-1]; len_stats[0] = max_b mel_lens, [1] = sum_b mel_lens
- * (len_stats must be zeroed by the caller or pass zero_stats=1). */
+ * cum[b,l] = inclusive prefix sum of reps; mel_lens[b] = cum[b,L-1]; len_stats[0] = max_b mel_lens, [1] = sum_b mel_lens,
+ * [2] = number of non-finite / > 1e6 durations (those contribute 0 frames; the reference raises on them).  The call zeroes len_stats. */
 typedef struct fs2_durations_args {
   const float* src; int use_target; float d_control; int B, L;
   float* d_rounded;     /* [B][L] or NULL */
   int32_t* cum;         /* [B][L] */
   int64_t* mel_lens;    /* [B] */
   int32_t* mel_lens32;  /* [B] or NULL */
-  int32_t* len_stats;   /* [2] */
+  int32_t* len_stats;   /* [3] */
 } fs2_durations_args;
 int fs2_durations(const fs2_durations_args* a, fs2_stream_t stream);
 
@@ -165,6 +165,23 @@ typedef struct fs2_conv_post_args {
   const float* x; int B, T, C; const float* w; const float* bias; int taps; float in_slope; float* wav;
 } fs2_conv_post_args;
 int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t stream);
+
+/* HiFi-GAN multi-receptive-field ResBlock group of one upsample stage as ONE persistent kernel (hifigan/models.py:154-160, ResBlock.forward
+ * :96-103):   y = (1/n_kernels) * sum_j R_j(x),   R_j: x <- conv_{k_j,1}( lrelu( conv_{k_j,dil_jd}( lrelu(x) ) + b1 ) ) + b2 + x  for d = 0..n_dil-1,
+ * lrelu slope 0.1, "same" zero padding at the utterance ends.  x, y: contiguous [B][N][C], C in {32, 64} (the 64- / 32-channel stages);
+ * every intermediate stays in shared / tensor memory (halo recompute), weights are the f16+f8 tiles of the per-layer kernel
+ * (FS2_TC_VARIANT_F8 with N = C: pack_conv_tc(w, f8=True)).  (k-1)*dil/2 <= 32 per conv.  Other shapes: FS2_ERR_UNSUPPORTED. */
+typedef struct fs2_resstack_args {
+  const float* x; float* y; int B, N, C;
+  int n_kernels, n_dil;
+  int k[FS2_MAX_DIL + 4]; int dil[FS2_MAX_DIL + 4][FS2_MAX_DIL];
+  const float *w1_tc[FS2_MAX_DIL + 4][FS2_MAX_DIL], *b1[FS2_MAX_DIL + 4][FS2_MAX_DIL];   /* dilated conv of each pair */
+  const float *w2_tc[FS2_MAX_DIL + 4][FS2_MAX_DIL], *b2[FS2_MAX_DIL + 4][FS2_MAX_DIL];   /* dilation-1 conv of each pair */
+} fs2_resstack_args;
+int fs2_resstack(const fs2_resstack_args* a, fs2_stream_t stream);
+/* launch plan (pure host logic): out[8] = {128-row tiles per slab, halo rows per side, output rows per work item, work items, grid,
+ * weight ring stages, dynamic shared memory bytes, TMEM columns} */
+int fs2_resstack_plan(const fs2_resstack_args* a, int num_sms, int32_t* out);
 
 /* x[b,t,:] += pos[t,:]   (decoder position add when the length regulator could not fuse it: frame-level variance configs) */
 int fs2_add_positions(float* x, const float* pos, int B, int T, int D, fs2_stream_t stream);
@@ -220,8 +237,8 @@ typedef struct fs2_encode_args {
   int32_t* mel_lens32;       /* [B] */
   int32_t* cum_dur;          /* [B][L] */
   float* x_adapted;          /* [B][L][D]: input of the length regulator */
-  int32_t* len_stats;        /* device [2]: max and sum of mel_lens */
-  int32_t* len_stats_host;   /* pinned host [2] or NULL: async D2H copy is enqueued on the stream */
+  int32_t* len_stats;        /* device [3]: max and sum of mel_lens, count of non-finite durations */
+  int32_t* len_stats_host;   /* pinned host [3] or NULL: async D2H copy is enqueued on the stream */
   void* workspace; size_t workspace_bytes;
 } fs2_encode_args;
 size_t fs2_encode_workspace_bytes(const fs2_acoustic_model* m, int B, int L);
@@ -259,6 +276,7 @@ typedef struct fs2_vocoder_model {
   const float *w_pre_tc, *w_up_a_tc[FS2_MAX_STAGES], *w_up_b_tc[FS2_MAX_STAGES];
   const float *w_rb1_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *w_rb2_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL];
   int f8_mask; /* bit 0: w_pre_tc, bit 1+i: every *_tc tile of stage i is in the f16+f8 format (FS2_TC_VARIANT_F8) */
+  int fused_mask; /* bit i: the ResBlock group of stage i runs as one fs2_resstack launch (needs f8_mask bit 1+i and 32 / 64 channels) */
 } fs2_vocoder_model;
 
 typedef struct fs2_vocoder_args {
@@ -275,7 +293,11 @@ int fs2_abi_version(void);                 /* bumps when any struct above change
 int64_t fs2_kernel_launch_count(void);     /* kernels launched by this library since load (process-wide) */
 const char* fs2_build_info(void);          /* "sm_100a ..." */
 size_t fs2_struct_size(int which);
-/* Per-kernel-class device timing for bench.py's roofline (CUDA events recorded around each launch on the launch stream).
+/* Re-entrancy: the library keeps no mutable process-wide state behind these calls except (a) a per-device table of one-time
+ * cudaFuncSetAttribute opt-ins and SM counts, filled under a mutex for the device that is CURRENT when a call is made -- make the
+ * device that owns the stream current before calling -- (b) the launch counter above and (c) the profiling state below, which is
+ * per host thread.  Tuning / tracing knobs exist only in builds with -DFS2_DEBUG_KNOBS.
+ * Per-kernel-class device timing for bench.py's roofline (CUDA events recorded around each launch on the launch stream).
  * Classes: 0 conv1d (implicit GEMM), 1 attention, 2 layernorm, 3 everything else.  begin() arms it, end() synchronises the
  * recorded events, fills ms/flops/launches per class (arrays of FS2_PROF_CLASSES) and disarms.  Not for timed regions. */
 #define FS2_PROF_CLASSES 4

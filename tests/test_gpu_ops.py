@@ -137,6 +137,48 @@ def test_conv1d_tensor_core_f8_split(case):
     assert err_exact < 1.5e-3, (err_contract, err_exact)       # ~2^-16 relative on O(1..10) outputs (single-pass fp16: ~2e-2 here)
 
 
+RESSTACK_CASES = [
+    # B, N, C, kernels, dilations
+    (1, 700, 32, (3, 7, 11), ((1, 3, 5),) * 3),       # two work items, ragged second tile
+    (2, 392 * 2, 32, (3, 7, 11), ((1, 3, 5),) * 3),   # exact multiple of the tile
+    (2, 100, 32, (3, 7, 11), ((1, 3, 5),) * 3),       # utterance shorter than the halo-extended slab
+    (2, 900, 64, (3, 7, 11), ((1, 3, 5),) * 3),       # 64 channels: three 128-row tiles per slab
+    (1, 264, 64, (3, 7, 11), ((1, 3, 5),) * 3),       # exactly one tile
+    (3, 50, 64, (3, 5), ((1, 2), (2, 6))),            # other kernel sets / dilation lists
+]
+
+
+@pytest.mark.parametrize("case", RESSTACK_CASES)
+def test_resstack_fused(case):
+    """fs2_resstack (one persistent kernel for a whole multi-receptive-field ResBlock group, intermediates on chip, halo recompute)
+    against an fp64 evaluation of hifigan/models.py:96-103,:154-160 with torch conv1d.  Error budget: the f16 + f8 operand split
+    (2^-16 relative per layer) through 6 layers per kernel size."""
+    import torch.nn.functional as F
+    B, N, C, kernels, dils = case
+    x = rnd(B, N, C, seed=21)
+    w1, b1, w2, b2 = [], [], [], []
+    want = torch.zeros(B, C, N, dtype=torch.float64)
+    for j, k in enumerate(kernels):
+        w1.append([]); b1.append([]); w2.append([]); b2.append([])
+        r = x.double().transpose(1, 2)
+        for d, dv in enumerate(dils[j]):
+            wa = rnd(C, C, k, seed=100 + 10 * j + d, scale=0.6 * (C * k) ** -0.5)      # [out, in, k]
+            wb = rnd(C, C, k, seed=200 + 10 * j + d, scale=0.6 * (C * k) ** -0.5)
+            ba, bb = rnd(C, seed=300 + 10 * j + d, scale=0.05), rnd(C, seed=400 + 10 * j + d, scale=0.05)
+            t = F.conv1d(F.leaky_relu(r, 0.1), wa.double(), ba.double(), dilation=dv, padding=(k - 1) * dv // 2)
+            t = F.conv1d(F.leaky_relu(t, 0.1), wb.double(), bb.double(), padding=(k - 1) // 2)
+            r = t + r
+            w1[j].append(packing.pack_conv_tc(packing.conv_w(wa), f8=True).to(DEV)); b1[j].append(ba.to(DEV))
+            w2[j].append(packing.pack_conv_tc(packing.conv_w(wb), f8=True).to(DEV)); b2[j].append(bb.to(DEV))
+        want += r
+    want = (want / len(kernels)).transpose(1, 2)
+    got = ops.resstack(x.to(DEV), kernels, dils, w1, b1, w2, b2)
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - want).abs().max().item()
+    assert torch.isfinite(got).all()
+    assert err < 3e-4 * max(1.0, want.abs().max().item()), (err, want.abs().max().item())
+
+
 def test_conv1d_tensor_core_alignment_contract():
     """The tcgen05 kernel reads activations with 256-bit loads: a 16-byte-but-not-32-byte aligned x is refused by the explicit
     backend and silently served by the exact fp32 kernel under FS2_CONV_AUTO (same contract, fp32 accuracy)."""
