@@ -138,6 +138,10 @@ class ResstackArgs(C.Structure):
                 ("w2_tc", (fp * MAX_DIL) * (MAX_DIL + 4)), ("b2", (fp * MAX_DIL) * (MAX_DIL + 4))]
 
 
+class WavInt16Args(C.Structure):
+    _fields_ = [("wav", fp), ("wav_batch_stride", i64), ("B", i32), ("N", i64), ("lens", fp), ("scale", f32), ("out", fp)]
+
+
 class VocoderArgs(C.Structure):
     _fields_ = [("B", i32), ("T", i32), ("mel", fp), ("mel_batch_stride", i64), ("mel_row_stride", i64),
                 ("wav", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
@@ -164,6 +168,7 @@ EXPORTS = {
     "fs2_length_regulate": (i32, [C.POINTER(LengthRegulateArgs), fp]),
     "fs2_conv_post": (i32, [C.POINTER(ConvPostArgs), fp]),
     "fs2_resstack": (i32, [C.POINTER(ResstackArgs), fp]),
+    "fs2_wav_to_int16": (i32, [C.POINTER(WavInt16Args), fp]),
     "fs2_resstack_plan": (i32, [C.POINTER(ResstackArgs), i32, C.c_void_p]),
     "fs2_transpose_bct_to_btc": (i32, [fp, fp, i32, i32, i32, fp]),
     "fs2_add_positions": (i32, [fp, fp, i32, i32, i32, fp]),

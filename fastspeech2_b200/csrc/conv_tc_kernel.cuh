@@ -359,16 +359,16 @@ __device__ __forceinline__ void tc_epilogue_dispatch(const TcP& p, uint32_t tmem
   }
 }
 
-// Operand scales of the f16 + f8 split (TcP::f8): activation lo * 2^12 and hi * 2 are rounded to E4M3; the packer stores
-// weight hi * 2^-12 and lo * 2^-1 in E4M3 (packing.pack_conv_tc), so both correction products carry the main term's scale.
-// |x| < 224 keeps the hi byte below E4M3's 448; beyond that the correction of that element saturates (the result degrades
-// towards single-pass fp16 accuracy for it, never to garbage).
+// Operand scales of the f16 + f8 split (TcP::f8): activation lo * 2^12 and hi (unscaled) are rounded to E4M3; the packer stores
+// weight hi * 2^-12 and lo (unscaled) in E4M3 (packing.pack_conv_tc), so both correction products carry the main term's scale.
+// |x| <= 448 stays inside E4M3; beyond that the correction of that element saturates (the result degrades towards single-pass
+// fp16 accuracy for it, never to garbage).
 constexpr float TC_F8_LO_SCALE = 4096.f;
-constexpr float TC_F8_HI_SCALE = 2.f;
+constexpr float TC_F8_HI_SCALE = 1.f;
 
 // One K-block of one transform thread: input activation, operand split, stores into the slab planes.
 //   F8 = false: plane 0 = fp16 hi, plane 1 = fp16 lo, both [16-byte K-chunk of 8 channels][row][8 halfs].
-//   F8 = true : plane 0 = fp16 hi as above; plane 1 = E4M3 [chunk 0: lo of the 16 channels | chunk 1: hi of the 16 channels][row][16 bytes]
+//   F8 = true : plane 0 = fp16 hi as above; plane 1 = E4M3 [chunk 0: lo * 2^12 of the 16 channels | chunk 1: hi of the 16 channels][row][16 bytes]
 //               -- the A operand of one K = 32 kind::f8f6f4 MMA whose B operand is [weight hi ; weight lo].
 template <bool LRELU, bool F8, int LD>
 __device__ __forceinline__ void tc_convert_store(const float (&src)[LD][8], const int (&rowu)[LD], const int (&offu)[LD], const int (&off8)[LD],
@@ -388,7 +388,7 @@ __device__ __forceinline__ void tc_convert_store(const float (&src)[LD][8], cons
       const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
       if (F8) {
         const uint32_t l8 = cvt_e4m3x2_sat((a0 - hf.x) * TC_F8_LO_SCALE, (a1 - hf.y) * TC_F8_LO_SCALE);   // a - hi is exact in fp32
-        const uint32_t h8 = cvt_e4m3x2_sat(hf.x * TC_F8_HI_SCALE, hf.y * TC_F8_HI_SCALE);
+        const uint32_t h8 = cvt_e4m3x2_sat(hf.x, hf.y);                                                    // TC_F8_HI_SCALE == 1
         if (j & 1) { lw[j >> 1] |= l8 << 16; lw[2 + (j >> 1)] |= h8 << 16; }
         else { lw[j >> 1] = l8; lw[2 + (j >> 1)] = h8; }
       } else {

@@ -84,6 +84,7 @@ int durations(const fs2_durations_args* a, cudaStream_t s);
 int length_regulate(const fs2_length_regulate_args* a, cudaStream_t s);
 int conv_post(const fs2_conv_post_args* a, cudaStream_t s);
 int resstack(const fs2_resstack_args* a, cudaStream_t s);
+int wav_to_int16(const fs2_wav_int16_args* a, cudaStream_t s);
 int resstack_plan(const fs2_resstack_args* a, int num_sms, int* out);
 int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t s);
 int add_positions(float* x, const float* pos, int B, int T, int D, cudaStream_t s);
@@ -408,6 +409,7 @@ size_t fs2_struct_size(int which) {
     case 12: return sizeof(fs2_vocoder_model);
     case 13: return sizeof(fs2_vocoder_args);
     case 14: return sizeof(fs2_resstack_args);
+    case 15: return sizeof(fs2_wav_int16_args);
     default: return 0;
   }
 }
@@ -456,6 +458,7 @@ int fs2_durations(const fs2_durations_args* a, fs2_stream_t st) { return duratio
 int fs2_length_regulate(const fs2_length_regulate_args* a, fs2_stream_t st) { return length_regulate(a, S(st)); }
 int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t st) { return conv_post(a, S(st)); }
 int fs2_resstack(const fs2_resstack_args* a, fs2_stream_t st) { return resstack(a, S(st)); }
+int fs2_wav_to_int16(const fs2_wav_int16_args* a, fs2_stream_t st) { return wav_to_int16(a, S(st)); }
 int fs2_resstack_plan(const fs2_resstack_args* a, int num_sms, int32_t* out) { return out ? resstack_plan(a, num_sms, out) : FS2_ERR_ARG; }
 int fs2_add_positions(float* x, const float* pos, int B, int T, int D, fs2_stream_t st) { return add_positions(x, pos, B, T, D, S(st)); }
 int fs2_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, fs2_stream_t st) {

@@ -400,4 +400,42 @@ int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaS
   return FS2_OK;
 }
 
+// ------------------------------------------------------------------ waveform -> int16 + per-utterance trim (utils/model.py:82-90)
+// out[b][t] = t < lens[b] ? (int16) trunc(wav[b][t] * scale) : 0.  numpy's astype("int16") truncates toward zero; values beyond the
+// int16 range (|wav| >= 1 after tanh: not reachable) are clamped instead of wrapping.  One thread converts 8 samples (16-byte store).
+__global__ void wav_to_int16_kernel(const float* __restrict__ wav, long long wav_bs, const long long* __restrict__ lens, float scale, int B,
+                                    long long N, short* __restrict__ out) {
+  const long long per_b = (N + 7) / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_b * B) return;
+  const int b = (int)(idx / per_b);
+  const long long t0 = (idx - (long long)b * per_b) * 8;
+  const long long len = lens ? min(max(lens[b], 0LL), N) : N;
+  const float* src = wav + (long long)b * wav_bs + t0;
+  short v[8];
+  if (t0 + 8 <= N && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = t0 + k < len ? (short)min(max(__float2int_rz(f[k] * scale), -32768), 32767) : (short)0;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (t0 + k < N && t0 + k < len) ? (short)min(max(__float2int_rz(src[k] * scale), -32768), 32767) : (short)0;
+  }
+  short* dst = out + (long long)b * N + t0;
+  if (t0 + 8 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+  } else {
+    for (int k = 0; k < 8 && t0 + k < N; k++) dst[k] = v[k];
+  }
+}
+
+int wav_to_int16(const fs2_wav_int16_args* a, cudaStream_t s) {
+  if (!a || !a->wav || !a->out || a->B <= 0 || a->N <= 0) return FS2_ERR_ARG;
+  const long long threads = ((a->N + 7) / 8) * a->B;
+  wav_to_int16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a->wav, (long long)a->wav_batch_stride, reinterpret_cast<const long long*>(a->lens), a->scale, a->B, (long long)a->N, reinterpret_cast<short*>(a->out));
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
 }  // namespace fs2

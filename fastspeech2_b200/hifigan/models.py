@@ -38,9 +38,12 @@ class Generator(nn.Module):
         # (2/3 of the tensor time, waveform error ~3e-5 of the 1e-4 bar when used everywhere), clear = three fp16 MMAs (~2e-6).
         # Default: the two wide, tensor-bound stages (256 / 128 channels, 64 % of the FLOPs); scripts/emul_split_precision.py.
         self.f8_mask = 0b00110
-        # Stages (bit i) whose ResBlock group runs as ONE persistent kernel with every intermediate on chip (fs2_resstack: the 64- and
-        # 32-channel stages); those stages use the f16 + f8 operand format regardless of f8_mask.
-        self.fused_mask = 0b1100
+        # Stages (bit i) whose ResBlock group runs as ONE persistent kernel with every intermediate on chip (fs2_resstack, available for
+        # the 64- and 32-channel stages; those stages use the f16 + f8 operand format regardless of f8_mask).  Default: the 32-channel
+        # stage, where it beats the 18 per-layer launches (5.7 vs 6.3 ms at B = 16 x 1012 frames, 27x less HBM traffic); on the
+        # 64-channel stage the three-tile slab leaves no room to overlap epilogues with MMAs and the per-layer path is faster
+        # (profiles/r02/resstack_*.txt), so it stays opt-in there (fused_mask |= 0b0100).
+        self.fused_mask = 0b1000
         populate(self, hifigan_spec(self._hd, weight_norm=True))
         with torch.no_grad():  # g = ||v|| so that the initial folded weight equals v, as torch's weight_norm does
             for base in self._bases():

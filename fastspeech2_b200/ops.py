@@ -146,6 +146,19 @@ def resstack(x, kernels, dilations, w1_tc, b1, w2_tc, b2):
     return y
 
 
+def wav_to_int16(wav, lengths=None, scale=32768.0, out=None):
+    """wav [B,N] fp32 (row-strided ok) -> int16 [B,N]: trunc(wav*scale), samples t >= lengths[b] zeroed (fs2_wav_to_int16)."""
+    _need_cuda(wav)
+    B, N = wav.shape
+    assert wav.stride(1) == 1
+    if out is None:
+        out = torch.empty(B, N, dtype=torch.int16, device=wav.device)
+    lens = None if lengths is None else lengths.to(device=wav.device, dtype=torch.long).contiguous()
+    a = L.WavInt16Args(wav=wav.data_ptr(), wav_batch_stride=wav.stride(0), B=B, N=N, lens=L.ptr(lens), scale=float(scale), out=out.data_ptr())
+    L.check(L.lib().fs2_wav_to_int16(C.byref(a), _stream(wav.device)), "fs2_wav_to_int16")
+    return out
+
+
 def transpose_bct_to_btc(x):
     _need_cuda(x)
     B, Cc, T = x.shape

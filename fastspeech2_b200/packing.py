@@ -51,7 +51,7 @@ def split_fp16(w: Tensor):
 
 
 F8_W_HI_SCALE = 2.0 ** -12      # weight hi -> E4M3 (pairs with the kernel's activation-lo scale 2^12, conv_tc_kernel.cuh)
-F8_W_LO_SCALE = 2.0 ** -1       # weight lo -> E4M3 (pairs with the activation-hi scale 2)
+F8_W_LO_SCALE = 1.0             # weight lo -> E4M3 (pairs with the unscaled activation hi)
 
 
 def _e4m3_bytes(x: Tensor) -> Tensor:
@@ -64,8 +64,8 @@ def pack_conv_tc(w: Tensor, f8: bool = False):
          128-byte header (float32[0] = 1/scale, int32[1] = format)  |  [N/NB][Cin/16][taps][2 planes][2 K-chunks][NB][16 bytes]
     Every (tap, 16-channel K-block) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major).
       f8 = False (format 0): plane 0 = fp16 hi, plane 1 = fp16 lo; a chunk row holds 8 channels.
-      f8 = True  (format 1, FS2_TC_VARIANT_F8): plane 0 = fp16 hi; plane 1 = E4M3 with chunk 0 = hi * 2^-12 and chunk 1 = lo * 2^-1 of the
-        K-block's 16 channels -- the B operand of one K = 32 kind::f8f6f4 MMA against the activations' [lo * 2^12 | hi * 2].
+      f8 = True  (format 1, FS2_TC_VARIANT_F8): plane 0 = fp16 hi; plane 1 = E4M3 with chunk 0 = hi * 2^-12 and chunk 1 = lo of the
+        K-block's 16 channels -- the B operand of one K = 32 kind::f8f6f4 MMA against the activations' [lo * 2^12 | hi].
     Returns None when the shape is not served by the tensor-core kernel."""
     taps, cin, n = w.shape
     nb = conv_tc_block(n)

@@ -48,9 +48,9 @@ enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POS
        /* the decoder's / PostNet's w_*_tc tiles are in the f16+f8 format (see FS2_TC_VARIANT_F8) */
        FS2_TC_DECODER_F8 = 16, FS2_TC_POSTNET_F8 = 32 };
 /* fs2_conv1d_args.tc_variant bits.  F8: w_tc holds the two-MMA operand split -- fp16 hi tiles as in the three-MMA split, and in
- * place of the fp16 lo tiles E4M3 tiles [hi * 2^-12 | lo * 2^-1] that one K = 32 kind::f8f6f4 MMA multiplies with the activations'
- * [lo * 2^12 | hi * 2]: y ~ a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo) with the bracket at E4M3 precision (relative error ~2^-16 instead
- * of ~2^-22; 2/3 of the tensor-pipe time and shared-memory operand traffic).  Activations beyond +-224 saturate in the correction. */
+ * place of the fp16 lo tiles E4M3 tiles [hi * 2^-12 | lo] that one K = 32 kind::f8f6f4 MMA multiplies with the activations'
+ * [lo * 2^12 | hi]: y ~ a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo) with the bracket at E4M3 precision (relative error ~2^-16 instead
+ * of ~2^-22; 2/3 of the tensor-pipe time and shared-memory operand traffic).  Activations beyond +-448 saturate in the correction. */
 enum { FS2_TC_VARIANT_F8 = 1 };
 
 /* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per work item,
@@ -179,9 +179,18 @@ typedef struct fs2_resstack_args {
   const float *w2_tc[FS2_MAX_DIL + 4][FS2_MAX_DIL], *b2[FS2_MAX_DIL + 4][FS2_MAX_DIL];   /* dilation-1 conv of each pair */
 } fs2_resstack_args;
 int fs2_resstack(const fs2_resstack_args* a, fs2_stream_t stream);
-/* launch plan (pure host logic): out[8] = {128-row tiles per slab, halo rows per side, output rows per work item, work items, grid,
- * weight ring stages, dynamic shared memory bytes, TMEM columns} */
+/* launch plan (pure host logic): out[11] = {128-row tiles per slab, halo rows per side, output rows per work item, work items, grid,
+ * weight ring stages, dynamic shared memory bytes, TMEM columns, rows per output TMA box, output boxes per tile, conv taps per weight stage} */
 int fs2_resstack_plan(const fs2_resstack_args* a, int num_sms, int32_t* out);
+
+/* out[b,t] = t < lens[b] ? (int16) trunc(wav[b,t] * scale) : 0   -- the device half of utils.model.vocoder_infer (utils/model.py:82-90:
+ * `(wavs.cpu().numpy() * max_wav_value).astype("int16")` then `wavs[i][:lengths[i]]`): 2 bytes per sample cross PCIe instead of 4, the
+ * trim is fused, and the copy can be asynchronous.  lens (samples, int64, device) may be NULL.  Values beyond int16 are clamped. */
+typedef struct fs2_wav_int16_args {
+  const float* wav; int64_t wav_batch_stride; int B; int64_t N;
+  const int64_t* lens; float scale; int16_t* out; /* [B][N] contiguous */
+} fs2_wav_int16_args;
+int fs2_wav_to_int16(const fs2_wav_int16_args* a, fs2_stream_t stream);
 
 /* x[b,t,:] += pos[t,:]   (decoder position add when the length regulator could not fuse it: frame-level variance configs) */
 int fs2_add_positions(float* x, const float* pos, int B, int T, int D, fs2_stream_t stream);

@@ -37,7 +37,7 @@ def test_struct_sizes_match_the_header():
     h = _lib.lib()
     table = {0: _lib.Conv1dArgs, 1: _lib.LayerNormArgs, 2: _lib.AttentionArgs, 3: _lib.EmbedArgs, 4: _lib.RowBiasArgs,
              5: _lib.VarianceHeadArgs, 6: _lib.DurationsArgs, 7: _lib.LengthRegulateArgs, 8: _lib.ConvPostArgs,
-             9: _lib.AcousticModel, 10: _lib.EncodeArgs, 11: _lib.DecodeArgs, 12: _lib.VocoderModel, 13: _lib.VocoderArgs, 14: _lib.ResstackArgs}
+             9: _lib.AcousticModel, 10: _lib.EncodeArgs, 11: _lib.DecodeArgs, 12: _lib.VocoderModel, 13: _lib.VocoderArgs, 14: _lib.ResstackArgs, 15: _lib.WavInt16Args}
     for i, cls in table.items():
         assert h.fs2_struct_size(i) == ctypes.sizeof(cls), cls.__name__
 
