@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--phonemes", type=int, default=128)
     ap.add_argument("--cpu-sample", type=int, default=2, help="utterances in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-full-batch", action="store_true", help="skip the one cold CPU pass over the whole batch (~45 s)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the extra BASELINE.json configs (0, 1, 3, 4-shard)")
     ap.add_argument("--voc-f8-mask", type=int, default=None, help="override hifigan.Generator.f8_mask (A/B of the operand split)")
     ap.add_argument("--voc-fused-mask", type=int, default=None, help="override hifigan.Generator.fused_mask (A/B of the fused ResBlock-group kernel)")
     ap.add_argument("--fs2-f8", type=int, default=None, choices=[0, 1], help="override the decoder / PostNet operand split (A/B)")
@@ -101,7 +103,7 @@ def workload_config(args, world, frames_per_utt):
                         "each (free-running, duration-steered random-init weights), FastSpeech2 + HiFi-GAN end to end, fp32 22.05 kHz waveform",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "phonemes": args.phonemes,
             "mel_frames_per_utt": round(frames_per_utt, 1),
-            "parallelism": f"dp{world}: utterance shards, weights replicated, no data-path collective; NCCL all-gather of the waveforms only",
+            "parallelism": f"dp{world}: utterance shards, weights replicated, no data-path collective; asynchronous NCCL gather of the waveforms to rank 0 only",
             "l2": "per-step activation working set (>2 GB) and weights (196 MB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -172,8 +174,15 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def fs2_flops_batch(src_lens, mel_lens):
+    """Algorithmic FastSpeech2 FLOPs of a batch with valid lengths (per utterance)."""
+    return float(sum(FS2_FLOPS(int(l), int(t)) for l, t in zip(src_lens, mel_lens)))
+
+
 def run_ours(args):
+    import contextlib
     import ctypes as C
+    import io
 
     import torch
     import torch.distributed as dist
@@ -181,7 +190,7 @@ def run_ours(args):
     from fastspeech2_b200 import _lib, configs, synth
     from fastspeech2_b200.hifigan import AttrDict, Generator
     from fastspeech2_b200.model import FastSpeech2
-    from fastspeech2_b200.parallel import gather_padded
+    from fastspeech2_b200.parallel import Rank0Gather
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,14 +204,19 @@ def run_ours(args):
         import datetime
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = _lib.lib()
+    pk = peaks()
+    scratch = tempfile.mkdtemp()
 
-    pc, mc = configs.make_configs("LJSpeech", tempfile.mkdtemp())
-    model = FastSpeech2(pc, mc)
-    model.load_state_dict(synth.fastspeech2_state_dict(pc, mc, seed=0))
-    if args.fs2_f8 is not None:
-        f8_bits = _lib.TC_DECODER_F8 | _lib.TC_POSTNET_F8
-        model.tc_mask = (model.tc_mask & ~f8_bits) | (f8_bits if args.fs2_f8 else 0)
-    model = model.to(dev).eval()
+    def acoustic(dataset):
+        pc, mc = configs.make_configs(dataset, scratch)
+        model = FastSpeech2(pc, mc)
+        model.load_state_dict(synth.fastspeech2_state_dict(pc, mc, seed=0))
+        if args.fs2_f8 is not None:
+            f8_bits = _lib.TC_DECODER_F8 | _lib.TC_POSTNET_F8
+            model.tc_mask = (model.tc_mask & ~f8_bits) | (f8_bits if args.fs2_f8 else 0)
+        return model.to(dev).eval()
+
+    model = acoustic("LJSpeech")
     voc = Generator(AttrDict(configs.HIFIGAN_CONFIG))
     voc.load_state_dict(synth.hifigan_state_dict(configs.HIFIGAN_CONFIG, seed=0))
     if args.voc_f8_mask is not None:
@@ -210,46 +224,18 @@ def run_ours(args):
     if args.voc_fused_mask is not None:
         voc.fused_mask = args.voc_fused_mask
     voc.eval()
-    import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         voc.remove_weight_norm()
     voc.to(dev)
 
-    spk_h, texts_h, lens_h, L = synth.make_batch(args.batch, args.phonemes, seed=rank)
-    spk_h, texts_h, lens_h = spk_h.pin_memory(), texts_h.pin_memory(), lens_h.pin_memory()
-    spk, texts, lens = spk_h.to(dev), texts_h.to(dev), lens_h.to(dev)
+    def inputs(batch, phonemes, seed, n_speakers=1, min_len=None):
+        spk, texts, lens, L = synth.make_batch(batch, phonemes, seed=seed, n_speakers=n_speakers, min_len=min_len)
+        host = tuple(t.pin_memory() for t in (spk, texts, lens))
+        return host, tuple(t.to(dev) for t in host), L
 
-    def step_local():                               # no collectives: safe to run on a single rank
-        out = model(spk, texts, lens, L)
-        wav = voc(out[1].transpose(1, 2))
-        return out, wav
-
-    def step_device():
-        out, wav = step_local()
-        if world > 1:
-            gather_padded(wav[:, 0], out[9])
-        return out, wav
-
-    def step_mel_only():
-        return model(spk, texts, lens, L)
-
-    wav_host = {}
-
-    def step_e2e():
-        s_d, t_d, l_d = spk_h.to(dev, non_blocking=True), texts_h.to(dev, non_blocking=True), lens_h.to(dev, non_blocking=True)
-        out = model(s_d, t_d, l_d, L)
-        wav = voc(out[1].transpose(1, 2))
-        if world > 1:
-            gather_padded(wav[:, 0], out[9])
-        key = tuple(wav.shape)
-        if key not in wav_host:
-            wav_host[key] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
-        wav_host[key].copy_(wav, non_blocking=True)
-        mel_lens_host = out[9].cpu()          # the step's result lengths (also the stream sync for the waveform copy)
-        return out, wav, mel_lens_host
-
-    def timed(fn, steps):
-        if world > 1:
+    def timed(fn, steps, collective=True):
+        """`steps` calls of fn bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks."""
+        if world > 1 and collective:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -260,67 +246,173 @@ def run_ours(args):
             last = fn()
         e1.record()
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 and collective:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         launches = torch.tensor([lib.fs2_kernel_launch_count() - n0], device=dev, dtype=torch.int64)
-        if world > 1:
+        if world > 1 and collective:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(launches, op=dist.ReduceOp.SUM)
         return ms.item(), int(launches.item()), last
 
+    def all_sum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ headline: configs[2], one micro-batch of `--batch` utterances per GPU per step
+    (spk_h, texts_h, lens_h), (spk, texts, lens), L = inputs(args.batch, args.phonemes, seed=rank)
+    gather = Rank0Gather() if world > 1 else None
+
+    def step_local():                               # no collectives: safe to run on a single rank
+        out = model(spk, texts, lens, L)
+        wav = voc(out[1].transpose(1, 2))
+        return out, wav
+
+    def step_device():
+        out, wav = step_local()
+        if gather is not None:
+            gather.submit(wav[:, 0], out[9])         # async, rank 0 receives; overlaps the next step
+        return out, wav
+
+    wav_host = {}
+
+    def step_e2e():
+        s_d, t_d, l_d = spk_h.to(dev, non_blocking=True), texts_h.to(dev, non_blocking=True), lens_h.to(dev, non_blocking=True)
+        out = model(s_d, t_d, l_d, L)
+        wav = voc(out[1].transpose(1, 2))
+        if gather is not None:
+            gather.submit(wav[:, 0], out[9])
+        key = tuple(wav.shape)
+        if key not in wav_host:
+            wav_host[key] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
+        wav_host[key].copy_(wav, non_blocking=True)
+        mel_lens_host = out[9].cpu()          # the step's result lengths (also the stream sync for the waveform copy)
+        return out, wav, mel_lens_host
+
     for _ in range(max(args.warmup, 3)):
         out, wav = step_device()
+    if gather is not None:
+        gather.flush()
     torch.cuda.synchronize()
-    frames_local = out[9].sum().to(torch.int64).reshape(1).clone()
-    if world > 1:
-        dist.all_reduce(frames_local, op=dist.ReduceOp.SUM)
-    frames_step = int(frames_local.item())                       # all ranks, one step
+    frames_step = int(all_sum(float(out[9].sum().item())))          # all ranks, one step
     samples_step = frames_step * HOP
+    fs2_flop_step = all_sum(fs2_flops_batch(lens_h.tolist(), out[9].tolist()))
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_total, launches, _ = timed(step_device, args.steps)
+    # N > 1: the asynchronous gather of the last step completes inside the timed region (flush before the closing event)
+    ms_total, launches, _ = timed(step_device, args.steps) if gather is None else _timed_with_flush(timed, step_device, gather, args.steps)
     clocks = sampler.stop() if sampler else None
     value = samples_step * args.steps / (ms_total * 1e-3)
 
-    ms_mel, _, _ = timed(step_mel_only, args.steps)
+    ms_mel, _, _ = timed(lambda: model(spk, texts, lens, L), args.steps)
     mel_fps = frames_step * args.steps / (ms_mel * 1e-3)
 
     for _ in range(2):
         step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    ms_e2e, _, _ = timed(step_e2e, args.steps) if gather is None else _timed_with_flush(timed, step_e2e, gather, args.steps)
     e2e_value = samples_step * args.steps / (ms_e2e * 1e-3)
     h2d = spk_h.numel() * 8 + texts_h.numel() * 8 + lens_h.numel() * 8
     d2h = int(wav.numel() * 4 + out[9].numel() * 8)
 
-    # ---- roofline of the dominant kernel class (conv1d implicit GEMM): one extra, untimed step with per-launch CUDA events
+    def class_profile(fn):
+        """One extra, untimed pass with CUDA events around every launch: per-class ms / flops / launches (fs2_profile_begin/end)."""
+        lib.fs2_profile_begin()
+        fn()
+        torch.cuda.synchronize()
+        n = _lib.PROF_CLASSES
+        ms = (C.c_double * n)(); fl = (C.c_double * n)(); cnt = (C.c_int64 * n)()
+        lib.fs2_profile_end(ms, fl, cnt)
+        return list(ms), list(fl), list(cnt)
+
+    def tensor_roofline(fn, ms_step):
+        """Roofline of the dominant kernel class = the tcgen05 kernels (implicit-GEMM conv1d + fused ResBlock group).  Bracketing every
+        launch with two events costs a bubble per launch, so the class's duration inside the TIMED region is its share of the
+        bracketed pass times the event-timed step; the raw bracketed figure is reported next to it."""
+        ms, fl, cnt = class_profile(fn)
+        share = ms[0] / max(sum(ms), 1e-9)
+        cls_ms = share * ms_step
+        achieved = fl[0] / (cls_ms * 1e-3) / 1e12 if cls_ms > 0 else 0.0
+        return {"achieved": achieved, "frac": achieved / pk["tflops_sustained"], "share_of_step": share, "launches_per_step": int(cnt[0]),
+                "avg_launch_ms": cls_ms / max(int(cnt[0]), 1), "algorithmic_tflop_per_step": fl[0] / 1e12,
+                "achieved_event_bracketed": fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0,
+                "other_classes_ms": {"attention": ms[1], "layernorm": ms[2], "other": ms[3], "conv1d_fp32_cuda_cores": ms[4]},
+                "other_classes_launches": {"attention": int(cnt[1]), "layernorm": int(cnt[2]), "other": int(cnt[3]), "conv1d_fp32_cuda_cores": int(cnt[4])}}
+
     roof = None
     if rank == 0:
-        lib.fs2_profile_begin()
-        step_local()                                # rank 0 only: must not contain a collective
-        torch.cuda.synchronize()
-        ms = (C.c_double * 4)(); fl = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
-        lib.fs2_profile_end(ms, fl, cnt)
-        pk = peaks()
-        # Bracketing every launch with two events costs a bubble per launch (the bracketed conv launches alone add up to more than
-        # the whole timed step), so the class's duration inside the TIMED region is taken as its share of the bracketed pass times
-        # the event-timed step; the raw bracketed figure is reported next to it.
-        bracketed = fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
-        share = ms[0] / max(sum(ms), 1e-9)
-        conv_ms = share * ms_total / args.steps
-        achieved = fl[0] / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        r = tensor_roofline(step_local, ms_total / args.steps)
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r02", "step_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roof = {"kernel": "conv1d implicit-GEMM (all launches of one step: FFT-block projections / conv-FFN, predictors, PostNet, HiFi-GAN convs)",
-                "bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops_sustained"], "peak_source": pk["source"] + ", bf16 sustained (kernel timed inside a long step)",
-                "traffic": traffic, "launches_per_step": int(cnt[0]), "avg_launch_ms": conv_ms / max(int(cnt[0]), 1),
-                "share_of_step": share, "achieved_event_bracketed": bracketed, "avg_launch_ms_event_bracketed": ms[0] / max(int(cnt[0]), 1),
-                "timing": "class share from one untimed step with CUDA events around every launch x the event-timed step",
-                "other_classes_ms": {"attention": ms[1], "layernorm": ms[2], "other": ms[3]},
-                "algorithmic_tflop_per_step": fl[0] / 1e12}
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("tcgen05_class_dram_bytes_per_launch"), tj.get("source")
+        roof = {"kernel": "tcgen05 kernel class: conv_tc_kernel (implicit-GEMM conv1d: FFT-block projections / conv-FFN, attention GEMMs, PostNet, HiFi-GAN "
+                          "convs) + resstack_kernel (fused ResBlock group); fp32 CUDA-core convs (encoder, predictors) are NOT counted",
+                "bound": "tensor", "achieved": r["achieved"], "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": r["frac"],
+                "peak_source": pk["source"] + ", bf16 sustained (kernels timed inside a long step); two MMAs per useful MMA-equivalent in the "
+                                              "f16+f8 operand split, three in the split-fp16 one: 0.50 / 0.33 of the peak is the ceiling",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "timing": "class share from one untimed step with CUDA events around every launch x the event-timed step", **{k: v for k, v in r.items() if k not in ("achieved", "frac")}}
+
+    # ------------------------------------------------------------------ the other BASELINE.json configs (N = 1: all of them; N > 1: the configs[4] shard)
+    extra_cfg = {}
+
+    def measure(name, workload, fn, flops_fn, steps, frames_fn, with_voc):
+        for _ in range(3):
+            o = fn()
+        torch.cuda.synchronize()
+        ms, _, o = timed(fn, steps)
+        frames = all_sum(frames_fn(o))
+        ms_step = ms / steps
+        flop = all_sum(flops_fn(o))
+        d = {"workload": workload, "ms_per_step": ms_step, "steps": steps, "mel_frames_per_s": frames / (ms_step * 1e-3),
+             "useful_tflops": flop / (ms_step * 1e-3) / 1e12, "frac_of_bf16_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["tflops_sustained"]}
+        if with_voc:
+            d["audio_samples_per_s"] = frames * HOP / (ms_step * 1e-3)
+        extra_cfg[name] = d
+
+    if not args.headline_only:
+        B4 = 64
+        (_, _, lens4_h), (spk4, texts4, lens4), L4 = inputs(B4, args.phonemes, seed=100 + rank)
+
+        def step_c4():
+            o = model(spk4, texts4, lens4, L4)
+            w = voc(o[1].transpose(1, 2))
+            return o
+
+        measure("configs[4]_shard", f"LJSpeech, {B4} utterances per GPU x {args.phonemes} phonemes (one GPU's shard of the batch-512 job; x{world} GPUs here), "
+                                    "FastSpeech2 + HiFi-GAN", step_c4,
+                lambda o: fs2_flops_batch(lens4_h.tolist(), o[9].tolist()) + HIFIGAN_FLOPS_PER_FRAME * float(o[9].sum().item()),
+                max(2, args.steps // 2), lambda o: float(o[9].sum().item()), True)
+        del spk4, texts4, lens4
+    if not args.headline_only and world == 1:
+        (_, _, lens1_h), (spk1, texts1, lens1), L1 = inputs(1, args.phonemes, seed=7)
+
+        def step_c0():
+            o = model(spk1, texts1, lens1, L1)
+            voc(o[1].transpose(1, 2))
+            return o
+
+        measure("configs[0]", f"LJSpeech, batch=1 x {args.phonemes} phonemes, FastSpeech2 + HiFi-GAN (latency case; the reference's CPU-runnable config)", step_c0,
+                lambda o: fs2_flops_batch(lens1_h.tolist(), o[9].tolist()) + HIFIGAN_FLOPS_PER_FRAME * float(o[9].sum().item()),
+                args.steps * 2, lambda o: float(o[9].sum().item()), True)
+        extra_cfg["configs[1]"] = {"workload": f"LJSpeech, batch={args.batch} x {args.phonemes} phonemes, FastSpeech2 only (mel, no vocoder)",
+                                   "ms_per_step": ms_mel / args.steps, "steps": args.steps, "mel_frames_per_s": mel_fps,
+                                   "useful_tflops": fs2_flop_step / (ms_mel / args.steps * 1e-3) / 1e12,
+                                   "frac_of_bf16_sustained_peak": fs2_flop_step / (ms_mel / args.steps * 1e-3) / 1e12 / pk["tflops_sustained"]}
+        libri = acoustic("LibriTTS")
+        (_, _, lens3_h), (spk3, texts3, lens3), L3 = inputs(64, 256, seed=11, n_speakers=904, min_len=64)
+
+        def step_c3():
+            return libri(spk3, texts3, lens3, L3)
+
+        measure("configs[3]", "LibriTTS multi-speaker (904-speaker embedding), batch=64, mixed 64-256 phonemes with padding masks, FastSpeech2 only; "
+                              "frames = VALID mel frames", step_c3,
+                lambda o: fs2_flops_batch(lens3_h.tolist(), o[9].tolist()), max(2, args.steps // 2), lambda o: float(o[9].sum().item()), False)
+        extra_cfg["configs[3]"]["padded_frames_per_step"] = int(step_c3()[0].shape[0] * step_c3()[0].shape[1])
+        del libri
 
     if rank == 0:
         cpu = None
@@ -331,6 +423,10 @@ def run_ours(args):
                    "sample": f"{n} of the {args.batch} utterances ({frames} mel frames), 1 warm-up + 1 timed pass ({sec:.1f} s), oracle port of "
                              "the reference (same ATen CPU kernels), fp32, best of {all, half, 32, 16} host threads",
                    "mel_frames_per_s_fastspeech2_only": fps}
+            if not args.no_cpu_full_batch:
+                sps_f, fps_f, sec_f, cores_f, frames_f = cpu_reference_run(args, args.batch, 1, 0)
+                cpu["full_batch_once"] = {"value": sps_f, "unit": "samples/s", "utterances": args.batch, "mel_frames": frames_f, "seconds": sec_f,
+                                          "cores": cores_f, "note": "the WHOLE configs[2] batch, one cold pass (no warm-up), same port"}
         line = {"metric": "audio_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -342,13 +438,28 @@ def run_ours(args):
                 "roofline": roof, "cpu_baseline": cpu,
                 "extra": {"mel_frames_per_s": frames_step * args.steps / (ms_total * 1e-3),
                           "fastspeech2_only_mel_frames_per_s": mel_fps, "fastspeech2_only_ms_per_step": ms_mel / args.steps,
-                          "algorithmic_tflop_per_step": (FS2_FLOPS(args.phonemes, frames_step / (args.batch * world)) * args.batch * world
-                                                         + HIFIGAN_FLOPS_PER_FRAME * frames_step) / 1e12,
-                          "operand_split": {"vocoder_f8_mask": int(voc.f8_mask), "vocoder_fused_stage_mask": int(voc.fused_mask), "fs2_tc_mask": int(model.tc_mask)},
+                          "algorithmic_tflop_per_step": (fs2_flop_step + HIFIGAN_FLOPS_PER_FRAME * frames_step) / 1e12,
+                          "useful_tflops_whole_step": (fs2_flop_step + HIFIGAN_FLOPS_PER_FRAME * frames_step) / (ms_total / args.steps * 1e-3) / 1e12,
+                          "configs": extra_cfg,
+                          "operand_split": {"vocoder_f8_mask": int(voc.f8_mask), "vocoder_fused_stage_mask": int(voc.fused_mask),
+                                            "fs2_tc_mask": int(model.tc_mask)},
                           "build": lib.fs2_build_info().decode()}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timed_with_flush(timed, step, gather, steps):
+    """Timed region for N > 1: the asynchronous rank-0 gather of the LAST step must complete inside the region."""
+    count = {"i": 0}
+
+    def fn():
+        r = step()
+        count["i"] += 1
+        if count["i"] == steps:
+            gather.flush()
+        return r
+    return timed(fn, steps)
 
 
 def main():

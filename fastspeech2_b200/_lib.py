@@ -18,6 +18,7 @@ CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
 TC_ENCODER, TC_PREDICTORS, TC_DECODER, TC_POSTNET = 1, 2, 4, 8
 TC_DECODER_F8, TC_POSTNET_F8 = 16, 32
 TC_VARIANT_F8 = 1
+PROF_CLASSES = 5
 
 fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 i32, i64, f32 = C.c_int, C.c_int64, C.c_float

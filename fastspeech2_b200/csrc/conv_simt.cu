@@ -235,7 +235,7 @@ int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s) {
   }
 #undef FS2_SIMT_LAUNCH
 #undef FS2_SIMT_ACT
-  prof_after(s, 0, 2.0 * a->B * a->T * (double)a->Cin * a->taps * a->N);
+  prof_after(s, 4, 2.0 * a->B * a->T * (double)a->Cin * a->taps * a->N);
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

@@ -435,7 +435,7 @@ int fs2_profile_end(double* ms, double* flops, int64_t* launches) {
     cudaError_t e = cudaEventSynchronize(r.b);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
     if (e != cudaSuccess) rc = FS2_ERR_CUDA - (int)e;
-    const int c = (r.cls >= 0 && r.cls < FS2_PROF_CLASSES) ? r.cls : FS2_PROF_CLASSES - 1;
+    const int c = (r.cls >= 0 && r.cls < FS2_PROF_CLASSES) ? r.cls : 3;
     ms[c] += t; flops[c] += r.flops; launches[c] += 1;
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }

@@ -307,9 +307,9 @@ size_t fs2_struct_size(int which);
  * device that owns the stream current before calling -- (b) the launch counter above and (c) the profiling state below, which is
  * per host thread.  Tuning / tracing knobs exist only in builds with -DFS2_DEBUG_KNOBS.
  * Per-kernel-class device timing for bench.py's roofline (CUDA events recorded around each launch on the launch stream).
- * Classes: 0 conv1d (implicit GEMM), 1 attention, 2 layernorm, 3 everything else.  begin() arms it, end() synchronises the
+ * Classes: 0 tcgen05 kernels (conv1d implicit GEMM + fused ResBlock group), 1 attention, 2 layernorm, 3 everything else, 4 fp32 CUDA-core conv1d.  begin() arms it, end() synchronises the
  * recorded events, fills ms/flops/launches per class (arrays of FS2_PROF_CLASSES) and disarms.  Not for timed regions. */
-#define FS2_PROF_CLASSES 4
+#define FS2_PROF_CLASSES 5
 int fs2_profile_begin(void);
 int fs2_profile_end(double* ms, double* flops, int64_t* launches);         /* sizeof of the i-th struct above, in declaration order (binding self-check) */
 

@@ -5,7 +5,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fastspeech2_b200.parallel import gather_padded, shard_microbatches
+from fastspeech2_b200.parallel import Rank0Gather, gather_padded, shard_microbatches
 
 
 def test_shard_microbatches_partition():
@@ -45,3 +45,37 @@ def test_gather_padded_world2():
         assert torch.equal(out[:2, :5], torch.arange(40, dtype=torch.float32).reshape(2, 5, 4))
         assert torch.all(out[:2, 5:] == 0)
         assert torch.equal(out[2:], torch.arange(64, dtype=torch.float32).reshape(2, 8, 4) + 1000)
+
+
+def _worker_rank0(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = Rank0Gather(align=4)
+    results = []
+    for step in range(3):                              # lengths differ per rank and per step; two buffers alternate
+        T = 6 + 2 * rank - step
+        local = torch.arange(2 * T, dtype=torch.float32).reshape(2, T) + 100 * rank + 1000 * step
+        g.submit(local, torch.tensor([T, T - 1], dtype=torch.int64))
+    g.flush()
+    q.put((rank, g.last()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank0_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_rank0, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[1] is None                              # only rank 0 receives
+    payload, lens = res[0]
+    assert lens.tolist() == [4, 3, 6, 5]               # step 2: T = 4 on rank 0, 6 on rank 1
+    assert payload.shape[0] == 4 and payload.shape[1] >= 8
+    assert torch.equal(payload[:2, :4], torch.arange(8, dtype=torch.float32).reshape(2, 4) + 2000)
+    assert torch.equal(payload[2:, :6], torch.arange(12, dtype=torch.float32).reshape(2, 6) + 2100)
