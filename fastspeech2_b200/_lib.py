@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LAYERS, MAX_POSTNET, MAX_STAGES, MAX_RESBLOCKS, MAX_DIL = 12, 8, 8, 32, 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
@@ -82,7 +82,7 @@ class FftBlockWeights(C.Structure):
 
 
 class PredictorWeights(C.Structure):
-    _fields_ = [(n, fp) for n in ("w_c1", "b_c1", "ln1_g", "ln1_b", "w_c2", "b_c2", "ln2_g", "ln2_b", "w_out", "b_out")]
+    _fields_ = [(n, fp) for n in ("w_c1", "b_c1", "ln1_g", "ln1_b", "w_c2", "b_c2", "ln2_g", "ln2_b", "w_out", "b_out", "w_c1_tc", "w_c2_tc")]
 
 
 class AcousticModel(C.Structure):

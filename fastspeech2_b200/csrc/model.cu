@@ -186,9 +186,10 @@ static int run_predictor(cudaStream_t s, const fs2_acoustic_model* m, const fs2_
                          const int32_t* lens, float control, const float* target, const float* bins, const float* emb, float* x_acc,
                          float* pred_out, float* h1, float* h2) {
   const int k = m->vp_kernel, D = m->d_model, VF = m->vp_filter;
-  FS2_TRY(conv(s, x, B, T, D, w.w_c1, nullptr, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
+  const bool tc = (m->tc_mask & FS2_TC_PREDICTORS) != 0;   // three-MMA split (fp32-class operands): these feed the discrete decisions
+  FS2_TRY(conv(s, x, B, T, D, w.w_c1, tc ? w.w_c1_tc : nullptr, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
   FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln1_g, w.ln1_b, nullptr));
-  FS2_TRY(conv(s, h2, B, T, VF, w.w_c2, nullptr, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
+  FS2_TRY(conv(s, h2, B, T, VF, w.w_c2, tc ? w.w_c2_tc : nullptr, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
   FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln2_g, w.ln2_b, nullptr));
   fs2_variance_head_args v{};
   v.h = h2; v.w = w.w_out; v.b = w.b_out; v.B = B; v.L = T; v.C = VF;
@@ -388,7 +389,7 @@ using namespace fs2;
 
 extern "C" {
 
-int fs2_abi_version(void) { return 5; }
+int fs2_abi_version(void) { return 6; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
 int fs2_conv_tc_plan(const fs2_conv1d_args* a, int num_sms, int32_t* out) { return conv_tc_plan_query(a, num_sms, out); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count.load(); }

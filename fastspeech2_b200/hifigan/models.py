@@ -35,9 +35,11 @@ class Generator(nn.Module):
         self._weight_norm = True
         self.use_tensor_cores = True     # split-FP16 tcgen05 kernel for every conv it supports; False = fp32 CUDA-core kernels only
         # Operand split per part (bit 0 = conv_pre, bit 1+i = upsample stage i): set = fp16 main term + one E4M3 correction MMA
-        # (2/3 of the tensor time, waveform error ~3e-5 of the 1e-4 bar when used everywhere), clear = three fp16 MMAs (~2e-6).
-        # Default: the two wide, tensor-bound stages (256 / 128 channels, 64 % of the FLOPs); scripts/emul_split_precision.py.
-        self.f8_mask = 0b00110
+        # (2/3 of the tensor time), clear = three fp16 MMAs.  Default: every upsample stage, NOT conv_pre -- measured with the shipped
+        # checkpoints (tests/test_gpu_model.py::test_hifigan_real_checkpoint_vs_reference, profiles/r02/parity_report_*.jsonl): all
+        # stages 1.0e-5 (LJSpeech) / 4.2e-5 (universal) of the 1e-4 bar, but conv_pre as well (its input is the raw log-mel, |x| up to
+        # 11.5) 1.2e-4 on the universal checkpoint.  CPU emulation of the split: scripts/emul_split_precision.py.
+        self.f8_mask = 0b11110
         # Stages (bit i) whose ResBlock group runs as ONE persistent kernel with every intermediate on chip (fs2_resstack, available for
         # the 64- and 32-channel stages; those stages use the f16 + f8 operand format regardless of f8_mask).  Default: the 32-channel
         # stage, where it beats the 18 per-layer launches (5.7 vs 6.3 ms at B = 16 x 1012 frames, 27x less HBM traffic); on the

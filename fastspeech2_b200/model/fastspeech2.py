@@ -52,6 +52,10 @@ class FastSpeech2(nn.Module):
         self.max_seq_len = int(model_config["max_seq_len"])
         # Which sub-networks may run on the split-FP16 tcgen05 kernel.  Encoder and predictors stay on the exact fp32 kernels:
         # they feed the discrete duration / pitch-bucket decisions (hard part 2) and are <1% of the FLOPs.
+        # Measured (scripts/flip_census.py, profiles/r02/flip_census_encoder_predictors.jsonl, 24.5k phonemes per config): against the
+        # CPU oracle the fp32 kernels flip 2 / 0 pitch-energy buckets (LJSpeech / LibriTTS) and no duration; the three-MMA tensor-core
+        # split (L.TC_ENCODER | L.TC_PREDICTORS, available and tested) flips 7 / 13 -- its truncating accumulator leaves 1.8e-5
+        # instead of 3.6e-6 on the predictions -- so it is not the default.
         # *_F8: those parts use the two-MMA operand split (fp16 main term + E4M3 correction, include/fs2b200.h FS2_TC_VARIANT_F8).
         self.tc_mask = L.TC_DECODER | L.TC_POSTNET | L.TC_DECODER_F8 | L.TC_POSTNET_F8
         self._packed = None          # (AcousticModel struct, keep-alive tensors, device)
@@ -117,7 +121,8 @@ class FastSpeech2(nn.Module):
         for nm in ("dur", "pitch", "energy"):
             dst = getattr(m, nm)
             for name, _ in L.PredictorWeights._fields_:
-                setattr(dst, name, P(f"{nm}.{name}"))
+                key = f"{nm}.{name}"
+                setattr(dst, name, P(key) if key in pk else 0)
         for name in ("pitch_bins", "energy_bins", "pitch_emb", "energy_emb", "w_mel", "b_mel"):
             setattr(m, name, P(name))
         m.tc_mask = self.tc_mask

@@ -167,6 +167,7 @@ def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet:
                                 g(p + ".1.running_mean"), g(p + ".1.running_var"))
         pk[f"post.{i}.w"], pk[f"post.{i}.b"] = conv_w(wf), bf.contiguous()
     tc_keys = [f"{side}.{i}.{w}" for side, n in (("enc", n_enc), ("dec", n_dec)) for i in range(n) for w in ("w_qkv", "w_o", "w_1", "w_2")]
+    tc_keys += [f"{nm}.{w}" for nm in ("dur", "pitch", "energy") for w in ("w_c1", "w_c2")]     # predictors: three-MMA split only
     post_keys = ["w_mel"] + [f"post.{i}.w" for i in range(n_postnet)]
     f8 = ([k for k in tc_keys if k.startswith("dec.")] if f8_decoder else []) + (post_keys if f8_postnet else [])
     add_tc_tiles(pk, tc_keys + post_keys, f8)

@@ -214,6 +214,7 @@ typedef struct fs2_predictor_weights {
   const float *w_c1, *b_c1, *ln1_g, *ln1_b; /* [k][D][F] */
   const float *w_c2, *b_c2, *ln2_g, *ln2_b; /* [k][F][F] */
   const float *w_out, *b_out;               /* [F], [1] */
+  const float *w_c1_tc, *w_c2_tc;           /* tensor-core tiles of the two convs (three-MMA split format), or NULL */
 } fs2_predictor_weights;
 
 typedef struct fs2_acoustic_model {
