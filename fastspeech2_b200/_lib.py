@@ -17,6 +17,7 @@ ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
 TC_ENCODER, TC_PREDICTORS, TC_DECODER, TC_POSTNET = 1, 2, 4, 8
 TC_DECODER_F8, TC_POSTNET_F8 = 16, 32
+TC_ATTENTION_GEMM = 64
 TC_VARIANT_F8 = 1
 PROF_CLASSES = 5
 

@@ -151,6 +151,20 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, int B, int T, int Tk,
 
 static inline long long at_tile_stride(int Tk) { return AT_HDR + (long long)Tk * 512; }   // 128 d x 2 planes x 2 bytes per key
 
+// K / V operand tiles of every (utterance, head) for the GEMM engine (also used by the fused kernel, attention_fused.cu)
+int pack_kv_tiles(const fs2_attention_args* a, unsigned char* kt, unsigned char* vt, long long tstride, cudaStream_t s) {
+  const int B = a->B, T = a->T, H = a->H;
+  const int Tk = (T + 127) / 128 * 128;
+  const long long nk = (long long)B * H * Tk * (AT_DH / 8), nv = (long long)B * H * (Tk / 8) * AT_DH;
+  prof_before(s);
+  pack_k_tiles_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(a->qkv, kt, B, T, Tk, H, tstride);
+  pack_v_tiles_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(a->qkv, vt, B, T, Tk, H, tstride);
+  prof_after(s, 1, 0.0);
+  g_launch_count++;
+  FS2_LAUNCH_CHECK();
+  return FS2_OK;
+}
+
 size_t attention_gemm_workspace(int B, int T, int H) {
   const int Tk = (T + 127) / 128 * 128;
   const size_t s_bytes = ((size_t)B * H * T * Tk * sizeof(float) + 255) & ~(size_t)255;
@@ -173,15 +187,7 @@ int attention_gemm(const fs2_attention_args* a, void* ws, size_t ws_bytes, cudaS
   unsigned char* kt = reinterpret_cast<unsigned char*>(base + s_bytes);
   unsigned char* vt = kt + tile_bytes;
 
-  {
-    const long long nk = (long long)B * H * Tk * (AT_DH / 8), nv = (long long)B * H * (Tk / 8) * AT_DH;
-    prof_before(s);
-    pack_k_tiles_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(a->qkv, kt, B, T, Tk, H, tstride);
-    pack_v_tiles_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(a->qkv, vt, B, T, Tk, H, tstride);
-    prof_after(s, 1, 0.0);
-    g_launch_count++;
-    FS2_LAUNCH_CHECK();
-  }
+  FS2_TRY(pack_kv_tiles(a, kt, vt, tstride, s));
   for (int h = 0; h < H; h++) {                        // S_h = Q_h K_h^T
     fs2_conv1d_args c{};
     c.x = a->qkv + h * AT_DH; c.x_batch_stride = (int64_t)T * 3 * D; c.x_row_stride = 3 * D;

@@ -35,7 +35,7 @@ inline int cuda_status() {
 constexpr int FS2_MAX_DEVICES = 64;
 struct DevState {
   std::atomic<int> num_sms{0};
-  std::atomic<bool> conv_tc_ready{false}, att_simt_ready{false}, fused_ready{false};
+  std::atomic<bool> conv_tc_ready{false}, att_simt_ready{false}, fused_ready{false}, att_fused_ready{false};
 };
 DevState* dev_state(int* err);                       // NULL + *err on failure
 struct DevOnce {                                     // RAII lock around a first-use setup section

@@ -59,6 +59,8 @@ int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s);
 int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaStream_t s, long long wt_batch_stride = 0);
 int attention_gemm(const fs2_attention_args* a, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t attention_gemm_workspace(int B, int T, int H);
+int attention_fused(const fs2_attention_args* a, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t attention_fused_workspace(int B, int T, int H);
 bool conv_tc_supported(const fs2_conv1d_args* a);
 int conv_tc_nb(int N);
 int conv_tc_plan_query(const fs2_conv1d_args* a, int num_sms, int* out);
@@ -144,8 +146,10 @@ static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_
   fs2_attention_args at{};
   at.qkv = f.qkv; at.ctx = f.ctx; at.B = B; at.T = T; at.H = m->n_head; at.Dh = D / m->n_head; at.key_lens = lens;
   at.scale = 1.0f / sqrtf((float)(D / m->n_head));
-  if (tc && f.att_ws && attention_gemm_usable(B, T, m->n_head)) {   // tensor-core path: S = QK^T and PV as split-FP16 GEMMs
-    FS2_TRY(attention_gemm(&at, f.att_ws, f.att_bytes, s));
+  if (tc && f.att_ws && (m->tc_mask & FS2_TC_ATTENTION_GEMM) && attention_gemm_usable(B, T, m->n_head)) {
+    FS2_TRY(attention_gemm(&at, f.att_ws, f.att_bytes, s));          // round-1 path: S materialised, two GEMM launches per head
+  } else if (tc && f.att_ws && T >= 128) {                            // one fused tcgen05 kernel: S stays in tensor memory, any length
+    FS2_TRY(attention_fused(&at, f.att_ws, f.att_bytes, s));
   } else {
     FS2_TRY(attention_simt(&at, s));
   }
@@ -169,8 +173,11 @@ static bool model_ok(const fs2_acoustic_model* m) {
 static FftBufs fft_bufs(Arena& ar, const fs2_acoustic_model* m, size_t rows, int B = 0, int T = 0, bool tc_attention = false) {
   FftBufs f;
   f.att_ws = nullptr; f.att_bytes = 0;
-  if (tc_attention && attention_gemm_usable(B, T, m->n_head)) {
+  if (tc_attention && (m->tc_mask & FS2_TC_ATTENTION_GEMM) && attention_gemm_usable(B, T, m->n_head)) {
     f.att_bytes = attention_gemm_workspace(B, T, m->n_head);
+    f.att_ws = ar.take(f.att_bytes);
+  } else if (tc_attention && T >= 128) {
+    f.att_bytes = attention_fused_workspace(B, T, m->n_head);
     f.att_ws = ar.take(f.att_bytes);
   }
   f.x = ar.f32(rows * m->d_model);
@@ -449,9 +456,14 @@ int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t st) { return conv1d_dispat
 int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t st) { return layernorm(a, S(st)); }
 int fs2_attention(const fs2_attention_args* a, fs2_stream_t st) {
   if (a && a->backend == 1) return attention_gemm(a, a->workspace, a->workspace_bytes, S(st));
+  if (a && a->backend == 2) return attention_fused(a, a->workspace, a->workspace_bytes, S(st));
   return attention_simt(a, S(st));
 }
-size_t fs2_attention_workspace_bytes(int B, int T, int H) { return (B > 0 && T > 0 && H > 0) ? attention_gemm_workspace(B, T, H) : 0; }
+size_t fs2_attention_workspace_bytes(int B, int T, int H) {      // enough for either tensor-core backend
+  if (!(B > 0 && T > 0 && H > 0)) return 0;
+  const size_t g = attention_gemm_workspace(B, T, H), f = attention_fused_workspace(B, T, H);
+  return g > f ? g : f;
+}
 int fs2_embed_positions(const fs2_embed_args* a, fs2_stream_t st) { return embed_positions(a, S(st)); }
 int fs2_add_speaker(const fs2_rowbias_args* a, fs2_stream_t st) { return add_speaker(a, S(st)); }
 int fs2_variance_head(const fs2_variance_head_args* a, fs2_stream_t st) { return variance_head(a, S(st)); }

@@ -46,7 +46,9 @@ enum { FS2_CONV_AUTO = 0, FS2_CONV_SIMT = 1, FS2_CONV_TC = 2 };
 /* which parts of the acoustic model may use the split-FP16 tcgen05 kernel (fs2_acoustic_model.tc_mask) */
 enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POSTNET = 8,
        /* the decoder's / PostNet's w_*_tc tiles are in the f16+f8 format (see FS2_TC_VARIANT_F8) */
-       FS2_TC_DECODER_F8 = 16, FS2_TC_POSTNET_F8 = 32 };
+       FS2_TC_DECODER_F8 = 16, FS2_TC_POSTNET_F8 = 32,
+       /* decoder attention through the round-1 GEMM path (scores materialised in HBM) instead of the fused kernel */
+       FS2_TC_ATTENTION_GEMM = 64 };
 /* fs2_conv1d_args.tc_variant bits.  F8: w_tc holds the two-MMA operand split -- fp16 hi tiles as in the three-MMA split, and in
  * place of the fp16 lo tiles E4M3 tiles [hi * 2^-12 | lo] that one K = 32 kind::f8f6f4 MMA multiplies with the activations'
  * [lo * 2^12 | hi]: y ~ a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo) with the bracket at E4M3 precision (relative error ~2^-16 instead
@@ -114,7 +116,8 @@ int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t stream);
 typedef struct fs2_attention_args {
   const float* qkv; float* ctx; int B, T, H, Dh;
   const int32_t* key_lens; float scale;
-  int backend;                  /* 0 = exact fp32 flash-style kernel; 1 = tensor-core path (split-FP16 GEMMs + row softmax), needs workspace */
+  int backend;                  /* 0 = exact fp32 flash-style kernel; 1 = tensor-core GEMMs + row softmax (scores in HBM, T <= 4096); 2 = ONE fused
+                                   tcgen05 kernel (QK^T, softmax, PV; scores stay in tensor memory, any T).  1 and 2 need the workspace */
   void* workspace; size_t workspace_bytes;   /* backend 1 only: >= fs2_attention_workspace_bytes(B, T, H) */
 } fs2_attention_args;
 int fs2_attention(const fs2_attention_args* a, fs2_stream_t stream);

@@ -272,6 +272,23 @@ def test_attention_tensor_core_path(T, lens):
     assert err < 2e-5, (err, err0)
 
 
+@pytest.mark.parametrize("T,lens", [(128, [128, 5, 77]), (300, [300, 129, 1]), (1017, [1017, 777, 513]), (1100, [1100, 64, 1037]), (4200, [4200, 4097, 9])])
+def test_attention_fused_kernel(T, lens):
+    """fs2_attention backend 2: QK^T, softmax and PV in ONE tcgen05 kernel (scores stay in tensor memory; two-pass softmax; no length
+    limit) against an fp64 evaluation of transformer/Modules.py:14-25 with the key mask of Models.py:79.  Same budget as the GEMM path."""
+    qkv = rnd(3, T, 768, seed=3)
+    kl = torch.tensor(lens, dtype=torch.int32)
+    want = E.attention(qkv.double(), 2, kl)
+    got = ops.attention(qkv.to(DEV), 2, kl.to(DEV), backend=2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    err = (got.cpu().double() - want).abs().max().item()
+    assert err < 2e-5, err
+    # padded query rows are written as exact zeros (contract of fs2_attention)
+    for b, n in enumerate(lens):
+        assert (got[b, n:] == 0).all()
+
+
 def test_embed_and_speaker():
     table = rnd(361, 256, seed=1)
     pos = rnd(1001, 256, seed=2)
