@@ -55,47 +55,92 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+_NVML_LOOP = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+out = open(sys.argv[2], "w")
+while True:
+    r = get_reasons(h)
+    out.write("%d,%d,%d,%.1f,%d\n" % (int(sys.argv[1]), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx, N.nvmlDeviceGetPowerUsage(h) / 1000.0, r))
+    out.flush()
+    time.sleep(0.1)
+"""
+
+
 class ClockSampler:
+    """SM clock, power and clock-event reasons every 100 ms while the bench runs.  NVML in a helper process (a handful of light driver
+    queries per sample); `nvidia-smi -lms` is the fallback -- its full query every 100 ms was observed to perturb the very region it
+    samples (device-timed step up to 1.5x the undisturbed one on some hosts), hence 500 ms there."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index: int):
         self.path = os.path.join(tempfile.mkdtemp(), "clocks.csv")
-        self.proc = None
+        self.proc, self.mode = None, None
+        phys = gpu_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                phys = int(vis.split(",")[gpu_index])
+            except Exception:
+                phys = gpu_index
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml  # noqa: F401
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_LOOP, str(phys), self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            self.mode = "nvml"
         except Exception:
-            self.proc = None
+            try:
+                self.f = open(self.path, "w")
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500",
+                                              "-i", str(phys)], stdout=self.f, stderr=subprocess.DEVNULL)
+                self.mode = "nvidia-smi"
+            except Exception:
+                self.proc = None
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler available"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        self.f.close()
         sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
+        try:
+            lines = open(self.path).read().splitlines()
+        except Exception:
+            lines = []
+        for line in lines:
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 8:
-                continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+                if self.mode == "nvml":
+                    if len(parts) < 5:
+                        continue
+                    sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+                    bits = int(parts[4])
+                    for b, n in self.BITS.items():
+                        if bits & b:
+                            reasons.add(n)
+                else:
+                    if len(parts) < 8:
+                        continue
+                    sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+                    for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
             except ValueError:
                 continue
-            for n, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "sampler": self.mode}
+        busy = [c for c, w in zip(sm, pw) if w > 250.0] or sm          # samples taken under load (idle draw is ~150 W)
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "samples_under_load": len(busy),
+                "reasons": sorted(reasons), "sampler": self.mode}
 
 
 def workload_config(args, world, frames_per_utt):

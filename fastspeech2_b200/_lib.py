@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LAYERS, MAX_POSTNET, MAX_STAGES, MAX_RESBLOCKS, MAX_DIL = 12, 8, 8, 32, 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
@@ -19,6 +19,7 @@ TC_ENCODER, TC_PREDICTORS, TC_DECODER, TC_POSTNET = 1, 2, 4, 8
 TC_DECODER_F8, TC_POSTNET_F8 = 16, 32
 TC_ATTENTION_GEMM = 64
 TC_VARIANT_F8 = 1
+TC_VARIANT_NB64 = 2
 PROF_CLASSES = 5
 
 fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
@@ -40,7 +41,7 @@ class Conv1dArgs(C.Structure):
 
 class LayerNormArgs(C.Structure):
     _fields_ = [("x", fp), ("y", fp), ("B", i32), ("T", i32), ("C", i32),
-                ("gamma", fp), ("beta", fp), ("eps", f32), ("row_lens", fp)]
+                ("gamma", fp), ("beta", fp), ("eps", f32), ("row_lens", fp), ("pre_relu", i32)]
 
 
 class AttentionArgs(C.Structure):

@@ -223,11 +223,14 @@ int conv1d_simt(const fs2_conv1d_args* a, cudaStream_t s) {
   }
 #define FS2_SIMT_LAUNCH(BN_, grid_)                   \
   if (small) { FS2_SIMT_ACT(64, BN_, grid_) } else { FS2_SIMT_ACT(128, BN_, grid_) }
-  if (a->N > 64) {
+  // narrow outputs on small problems (FFN w_2, predictor convs: 2048 rows x 256 channels): 64-column CTAs double the CTA count
+  // (64 -> 128 on 148 SMs)
+  const bool narrow_small = small && a->N > 64 && (long long)gx * ((a->N + 127) / 128) < 148;
+  if (a->N > 64 && !narrow_small) {
     dim3 grid((unsigned)gx, (a->N + 127) / 128);
     FS2_SIMT_LAUNCH(128, grid)
   } else if (a->N > 32) {
-    dim3 grid((unsigned)gx, 1);
+    dim3 grid((unsigned)gx, (a->N + 63) / 64);
     FS2_SIMT_LAUNCH(64, grid)
   } else {
     dim3 grid((unsigned)gx, 1);

@@ -52,13 +52,16 @@ static constexpr int g_tc_tune[4] = {0, 0, 0, 0};
 // tensor memory budget, grid.  Returns FS2_OK or FS2_ERR_UNSUPPORTED.  Exposed as fs2_conv_tc_plan so that the heuristics'
 // invariants are testable without a GPU (tests/test_abi.py).
 static int conv_tc_plan(const fs2_conv1d_args* a, int num_sms, TcP& p, size_t& smem, int& grid) {
-  p.NB = conv_tc_nb(a->N);
+  const bool nb64 = (a->tc_variant & FS2_TC_VARIANT_NB64) != 0;   // 64-channel work items: separate accumulators for hi*hi and the cross terms
+  p.NB = nb64 ? (a->N % 64 == 0 ? 64 : (a->N < 64 && a->N % 16 == 0 ? a->N : 0)) : conv_tc_nb(a->N);
+  if (p.NB == 0) return FS2_ERR_UNSUPPORTED;
   p.acc_stride = (p.NB + 31) & ~31;
   const int halo = (a->taps - 1) * a->dilation;
   const int tiles128 = (a->T + 127) / 128;
   int mt = 2;                                          // two accumulator sets of MT tiles: 2*MT*TG*acc_stride <= 512 columns
   if (p.acc_stride <= 64 && tiles128 >= 4 && 4 * 128 + halo <= 5 * TC_TTHREADS / TC_CHUNKS) mt = 4;   // narrow layers: amortise per-item handshakes
   if (g_tc_tune[3] == -1) mt = 2;                      // debug: force MT = 2
+  if (nb64 && mt > 2) mt = 2;                          // keeps TG = 2 (two accumulator sets of MT*2 tiles of 64 columns = 512)
   if (mt > tiles128) mt = tiles128 >= 2 ? 2 : 1;
   if (mt == 2 && mt * 128 + halo > TC_LD * TC_TTHREADS / TC_CHUNKS) mt = 1;   // rows one register-ring slot can hold
   // small problems (decoder projections, attention PV): prefer more, smaller work items when MT = 2 would leave SMs idle

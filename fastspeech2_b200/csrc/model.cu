@@ -123,9 +123,44 @@ static int conv(cudaStream_t s, const float* x, int B, int T, int Cin, const flo
   return conv1d_dispatch(&a, s);
 }
 
-static int ln(cudaStream_t s, const float* x, float* y, int B, int T, int C, const float* g, const float* b, const int32_t* lens) {
-  fs2_layernorm_args a{x, y, B, T, C, g, b, 1e-5f, lens};
+static int ln(cudaStream_t s, const float* x, float* y, int B, int T, int C, const float* g, const float* b, const int32_t* lens,
+              int pre_relu = 0) {
+  fs2_layernorm_args a{x, y, B, T, C, g, b, 1e-5f, lens, pre_relu};
   return layernorm(&a, s);
+}
+
+// K-segmented tensor-core convolution for the layers that feed the discrete decisions (encoder, predictors): the sum over taps and
+// input channels is cut into (tap, 256-channel) slices; each slice is one tcgen05 launch of 16 K-steps with separate accumulators for
+// the hi*hi term and the cross terms (FS2_TC_VARIANT_NB64), and the slices are added in fp32 round-to-nearest by the epilogue's
+// accumulate path.  That bounds the tensor core's truncating accumulation to 16 steps per chain (a single k = 9 launch has 432) and
+// brings the error back to the fp32 CUDA-core kernel's level (profiles/r02/flip_census_*.jsonl).  `w_seg`: taps * (Cin/256) tile
+// buffers of 128 + 1024*N bytes (packing.pack_conv_tc_segments).  y = bias + sum_slices + res, rows >= row_lens zeroed; no output
+// activation (a following ReLU is applied by the consumer: in_act of the next conv / pre_relu of the LayerNorm).
+static int conv_seg(cudaStream_t s, const float* x, int B, int T, int Cin, const float* w_seg, const float* bias, int N, int taps, int pad,
+                    float* y, const float* res, int in_act, float in_slope, const int32_t* row_lens) {
+  constexpr int SEG = 256;
+  if (Cin % SEG || N % 64) return FS2_ERR_UNSUPPORTED;
+  const int nkc = Cin / SEG, nseg = taps * nkc;
+  const size_t seg_bytes = 128 + (size_t)1024 * N;
+  for (int tap = 0; tap < taps; tap++)
+    for (int kc = 0; kc < nkc; kc++) {
+      const int idx = tap * nkc + kc;
+      fs2_conv1d_args a{};
+      a.x = x + kc * SEG; a.x_batch_stride = (int64_t)T * Cin; a.x_row_stride = Cin;
+      a.B = B; a.T = T; a.Cin = SEG;
+      a.w = nullptr; a.w_tc = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(w_seg) + idx * seg_bytes);
+      a.backend = FS2_CONV_TC; a.tc_variant = FS2_TC_VARIANT_NB64;
+      a.bias = idx == 0 ? bias : nullptr;
+      a.N = N; a.taps = 1; a.dilation = 1; a.pad_left = pad - tap;
+      a.in_act = in_act; a.in_slope = in_slope; a.out_act = FS2_ACT_NONE;
+      const bool last = idx == nseg - 1;
+      a.res = last ? res : nullptr; a.res_batch_stride = (int64_t)T * N; a.res_row_stride = N;
+      a.alpha = 1.f; a.accumulate = idx > 0;
+      a.row_lens = last ? row_lens : nullptr;
+      a.y = y; a.y_batch_stride = (int64_t)T * N; a.y_row_stride = N;
+      FS2_TRY(conv1d_tc(&a, a.w_tc, a.tc_variant, s));
+    }
+  return FS2_OK;
 }
 
 struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; void* att_ws; size_t att_bytes; };
@@ -138,9 +173,24 @@ static bool attention_gemm_usable(int B, int T, int H) {
 
 // One FFT block in place on bufs.x  (transformer/Layers.py:21-30)
 static int fft_block(cudaStream_t s, const fs2_acoustic_model* m, const fs2_fft_block_weights& w, const FftBufs& f, int B, int T,
-                     const int32_t* lens, bool tc, unsigned tcv) {
+                     const int32_t* lens, bool tc, unsigned tcv, bool segmented = false) {
   const int D = m->d_model, F = m->d_inner;
   const float* none = nullptr;
+  if (segmented) {                                     // encoder on the tensor cores: K-segmented convs, exact attention
+    if (!w.w_qkv_tc || !w.w_o_tc || !w.w_1_tc || !w.w_2_tc || m->k2 != 1) return FS2_ERR_ARG;
+    FS2_TRY(conv_seg(s, f.x, B, T, D, w.w_qkv_tc, w.b_qkv, 3 * D, 1, 0, f.qkv, nullptr, FS2_ACT_NONE, 0.f, nullptr));
+    fs2_attention_args at{};
+    at.qkv = f.qkv; at.ctx = f.ctx; at.B = B; at.T = T; at.H = m->n_head; at.Dh = D / m->n_head; at.key_lens = lens;
+    at.scale = 1.0f / sqrtf((float)(D / m->n_head));
+    FS2_TRY(attention_simt(&at, s));
+    FS2_TRY(conv_seg(s, f.ctx, B, T, D, w.w_o_tc, w.b_o, D, 1, 0, f.tmp, f.x, FS2_ACT_NONE, 0.f, nullptr));
+    FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln1_g, w.ln1_b, lens));
+    // conv-FFN: w_1 leaves the pre-activation hidden, the ReLU is w_2's input activation (leaky_relu with slope 0)
+    FS2_TRY(conv_seg(s, f.x, B, T, D, w.w_1_tc, w.b_1, F, m->k1, (m->k1 - 1) / 2, f.hid, nullptr, FS2_ACT_NONE, 0.f, nullptr));
+    FS2_TRY(conv_seg(s, f.hid, B, T, F, w.w_2_tc, w.b_2, D, 1, 0, f.tmp, f.x, FS2_ACT_LRELU, 0.f, nullptr));
+    FS2_TRY(ln(s, f.tmp, f.x, B, T, D, w.ln2_g, w.ln2_b, lens));
+    return FS2_OK;
+  }
   FS2_TRY(conv(s, f.x, B, T, D, w.w_qkv, tc ? w.w_qkv_tc : none, w.b_qkv, 3 * D, 1, 1, 0, FS2_ACT_NONE, 0.f, f.qkv, nullptr, FS2_ACT_NONE, 0.f,
                1.f, 0, nullptr, tcv));
   fs2_attention_args at{};
@@ -193,11 +243,17 @@ static int run_predictor(cudaStream_t s, const fs2_acoustic_model* m, const fs2_
                          const int32_t* lens, float control, const float* target, const float* bins, const float* emb, float* x_acc,
                          float* pred_out, float* h1, float* h2) {
   const int k = m->vp_kernel, D = m->d_model, VF = m->vp_filter;
-  const bool tc = (m->tc_mask & FS2_TC_PREDICTORS) != 0;   // three-MMA split (fp32-class operands): these feed the discrete decisions
-  FS2_TRY(conv(s, x, B, T, D, w.w_c1, tc ? w.w_c1_tc : nullptr, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
-  FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln1_g, w.ln1_b, nullptr));
-  FS2_TRY(conv(s, h2, B, T, VF, w.w_c2, tc ? w.w_c2_tc : nullptr, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
-  FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln2_g, w.ln2_b, nullptr));
+  if ((m->tc_mask & FS2_TC_PREDICTORS) && w.w_c1_tc && w.w_c2_tc) {   // tensor cores, K-segmented (conv_seg); ReLU applied by the LayerNorm
+    FS2_TRY(conv_seg(s, x, B, T, D, w.w_c1_tc, w.b_c1, VF, k, (k - 1) / 2, h1, nullptr, FS2_ACT_NONE, 0.f, nullptr));
+    FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln1_g, w.ln1_b, nullptr, 1));
+    FS2_TRY(conv_seg(s, h2, B, T, VF, w.w_c2_tc, w.b_c2, VF, k, 1, h1, nullptr, FS2_ACT_NONE, 0.f, nullptr));   // padding=1 is hard-coded upstream
+    FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln2_g, w.ln2_b, nullptr, 1));
+  } else {
+    FS2_TRY(conv(s, x, B, T, D, w.w_c1, nullptr, w.b_c1, VF, k, 1, (k - 1) / 2, FS2_ACT_RELU, 0.f, h1));
+    FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln1_g, w.ln1_b, nullptr));
+    FS2_TRY(conv(s, h2, B, T, VF, w.w_c2, nullptr, w.b_c2, VF, k, 1, 1, FS2_ACT_RELU, 0.f, h1));  // padding=1 is hard-coded upstream
+    FS2_TRY(ln(s, h1, h2, B, T, VF, w.ln2_g, w.ln2_b, nullptr));
+  }
   fs2_variance_head_args v{};
   v.h = h2; v.w = w.w_out; v.b = w.b_out; v.B = B; v.L = T; v.C = VF;
   v.lens = lens; v.control = control; v.target = target;
@@ -218,7 +274,7 @@ static int encode_impl(const fs2_acoustic_model* m, const fs2_encode_args* a, cu
 
   fs2_embed_args e{a->texts, m->word_emb, m->enc_pos, f.x, B, L, D, m->n_vocab};
   FS2_TRY(embed_positions(&e, s));
-  for (int i = 0; i < m->n_enc; i++) FS2_TRY(fft_block(s, m, m->enc[i], f, B, L, a->src_lens, (m->tc_mask & FS2_TC_ENCODER) != 0, 0));
+  for (int i = 0; i < m->n_enc; i++) FS2_TRY(fft_block(s, m, m->enc[i], f, B, L, a->src_lens, false, 0, (m->tc_mask & FS2_TC_ENCODER) != 0));
   if (m->spk_emb) {
     if (!a->speakers) return FS2_ERR_ARG;
     fs2_rowbias_args r{f.x, m->spk_emb, a->speakers, B, L, D, m->n_speakers};
@@ -396,7 +452,7 @@ using namespace fs2;
 
 extern "C" {
 
-int fs2_abi_version(void) { return 6; }
+int fs2_abi_version(void) { return 7; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
 int fs2_conv_tc_plan(const fs2_conv1d_args* a, int num_sms, int32_t* out) { return conv_tc_plan_query(a, num_sms, out); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count.load(); }

@@ -35,7 +35,7 @@
 namespace fs2 {
 
 constexpr int RS_MAXK = FS2_MAX_DIL + 4;   // kernel sizes per stage
-constexpr int RS_THREADS = 320;
+constexpr int RS_THREADS_MAX = 64 + 16 * 32;   // producer + MMA warps, up to 16 row warps
 constexpr int RS_GUARD = 1024;             // zeroed bytes in front of the first slab (taps reach up to 32 rows before row 0)
 constexpr int RS_SB_MAX = 16;
 
@@ -72,7 +72,8 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, int c0,
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_reads() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 row warps only
+template <int NTHREADS>
+__device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }   // the row warps only
 // byte offset of 16-byte chunk c of row r inside a [rows][128 B] box written / read by TMA with CU_TENSOR_MAP_SWIZZLE_128B
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -117,11 +118,15 @@ __device__ __forceinline__ void rs_store16(unsigned char* kblk, uint32_t chunk_b
 __device__ __forceinline__ float rs_lrelu(float v) { return fmaxf(v, 0.1f * v); }   // LRELU_SLOPE = 0.1 (hifigan/models.py:7)
 
 template <int C, int MT>
-__global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+__global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                                                                  const RsP p) {
-  constexpr int KB = C / 16, R = MT * 128, HC = C / 2, NG = HC / 16;   // NG: 16-channel groups per row warp
+  // one row warp per (TMEM lane quarter, 16-channel column group): 8 warps for 32 channels, 16 for 64 -- the epilogue is the
+  // critical path between a conv's MMAs and the next conv's, so its latency is cut by spreading a row's columns over more warps
+  constexpr int KB = C / 16, R = MT * 128, HC = 16, NG = 1, NRW = 4 * KB, RS_THREADS = 64 + 32 * NRW;
   constexpr int NH = C / 32;                                           // 32-channel (128-byte) column blocks of a row
-  constexpr int G0N = 2;                                               // tiles in the first MMA group ({0,1} | the rest)
+  // tiles in the first MMA group.  The next conv's first group needs the epilogues of tiles 0 .. G0N: with a 3-tile slab {0} | {1,2}
+  // lets it start after ONE tile's epilogue beyond the MMAs ({0,1} | {2} needed all three); with 4 tiles {0,1} | {2,3}.
+  constexpr int G0N = MT == 3 ? 1 : 2;
   // Alternative kept for experiments: with 32 channels a whole conv's weight stages fit in the ring, so they can be streamed ONCE and
   // the MMAs issued tile by tile (tile m of the next conv starts as soon as tiles m-1 .. m+1 are through their epilogue).  Measured
   // slower than the two-group schedule (6.43 vs 5.67 ms on the 32-channel stage, profiles/r02/resstack_bench_*.txt): the single
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
   for (int i = tid; i < RS_GUARD / 16; i += RS_THREADS) reinterpret_cast<uint4*>(smem0)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < RS_SB_MAX; i++) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < 4; i++) { mbar_init(&accFull[i], 1); mbar_init(&rowsReady[i], 8); }
+    for (int i = 0; i < 4; i++) { mbar_init(&accFull[i], 1); mbar_init(&rowsReady[i], NRW); }
     mbar_init(xLoaded, 1); mbar_init(xaFree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(&rowsReady[m]);
         }
-        row_warps_sync();        // every warp has finished reading the boxes: conv1's epilogue may overwrite XT
+        row_warps_sync<32 * NRW>();        // every warp has finished reading the boxes: conv1's epilogue may overwrite XT
         for (int d = 0; d < p.n_dil; d++) {
           const bool last = d == p.n_dil - 1;
           for (int c2 = 0; c2 < 2; c2++) {
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
         }
         // ---- result boxes -> y: store for the first kernel size, reduce-add (in L2) for the others; rows beyond N are clipped by the TMA
         fence_proxy_async();
-        row_warps_sync();
+        row_warps_sync<32 * NRW>();
         if (io) {
           tma_wait_all();        // the previous kernel size's boxes are complete in L2 before this one's reduce-add (a round earlier: no wait in practice)
           for (int hh = 0; hh < NH; hh++)
@@ -568,8 +573,8 @@ int resstack(const fs2_resstack_args* a, cudaStream_t s) {
   FS2_TRY(make_map(&tmx, a->x, a->B, a->N, a->C, 128));
   FS2_TRY(make_map(&tmy, a->y, a->B, a->N, a->C, p.OBOX));
   prof_before(s);
-  if (a->C == 32) resstack_kernel<32, 4><<<plan[4], RS_THREADS, plan[6], s>>>(tmx, tmy, p);
-  else resstack_kernel<64, 3><<<plan[4], RS_THREADS, plan[6], s>>>(tmx, tmy, p);
+  if (a->C == 32) resstack_kernel<32, 4><<<plan[4], 64 + 8 * 32, plan[6], s>>>(tmx, tmy, p);
+  else resstack_kernel<64, 3><<<plan[4], 64 + 8 * 64, plan[6], s>>>(tmx, tmy, p);
   prof_after(s, 0, flops);
   FS2_LAUNCH_CHECK();
   return FS2_OK;

@@ -90,7 +90,7 @@ int add_positions(float* x, const float* pos, int B, int T, int D, cudaStream_t 
 // One warp per row; the row lives in registers (C <= 1024), two-pass mean / variance like ATen's CPU kernel.
 __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int T, int C4,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                 const int* __restrict__ row_lens) {
+                                 const int* __restrict__ row_lens, int pre_relu) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -110,6 +110,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict_
     const int c = lane + i * 32;
     if (c < C4) {
       v[i] = in[c];
+      if (pre_relu) v[i] = make_float4(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f), fmaxf(v[i].z, 0.f), fmaxf(v[i].w, 0.f));
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -145,7 +146,7 @@ int layernorm(const fs2_layernorm_args* a, cudaStream_t s) {
   if (rows > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   prof_before(s);
   layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a->x, a->y, (int)rows, a->T, a->C / 4, a->gamma, a->beta, a->eps,
-                                                             a->row_lens);
+                                                             a->row_lens, a->pre_relu);
   prof_after(s, 2, 0.0);
   FS2_LAUNCH_CHECK();
   return FS2_OK;

@@ -50,14 +50,15 @@ class FastSpeech2(nn.Module):
                         torch.exp(torch.linspace(np.log(stats["energy"][0]), np.log(stats["energy"][1]), n)))
         self.multi_speaker = bool(model_config["multi_speaker"])
         self.max_seq_len = int(model_config["max_seq_len"])
-        # Which sub-networks may run on the split-FP16 tcgen05 kernel.  Encoder and predictors stay on the exact fp32 kernels:
-        # they feed the discrete duration / pitch-bucket decisions (hard part 2) and are <1% of the FLOPs.
-        # Measured (scripts/flip_census.py, profiles/r02/flip_census_encoder_predictors.jsonl, 24.5k phonemes per config): against the
-        # CPU oracle the fp32 kernels flip 2 / 0 pitch-energy buckets (LJSpeech / LibriTTS) and no duration; the three-MMA tensor-core
-        # split (L.TC_ENCODER | L.TC_PREDICTORS, available and tested) flips 7 / 13 -- its truncating accumulator leaves 1.8e-5
-        # instead of 3.6e-6 on the predictions -- so it is not the default.
-        # *_F8: those parts use the two-MMA operand split (fp16 main term + E4M3 correction, include/fs2b200.h FS2_TC_VARIANT_F8).
-        self.tc_mask = L.TC_DECODER | L.TC_POSTNET | L.TC_DECODER_F8 | L.TC_POSTNET_F8
+        # Which sub-networks run on the tcgen05 kernels (L.TC_* bits; cleared = exact fp32 CUDA-core kernels).
+        #  * decoder FFT blocks, mel_linear, PostNet: two-MMA operand split (*_F8: fp16 main term + one E4M3 correction MMA), fused attention.
+        #  * encoder FFT blocks and the three variance predictors feed the DISCRETE duration / pitch / energy-bucket decisions (SURVEY.md
+        #    section 7, hard part 2).  A single long tensor-core accumulation (432 truncating steps for the k = 9 conv) left 1.8e-5 on the
+        #    predictions and flipped 7 / 13 buckets per 24.5k phonemes (fp32 kernels: 3.6e-6, 2 / 0).  They therefore run K-SEGMENTED
+        #    (fs2b200.h: every (tap, 256-channel) slice is its own 16-step launch with a separate hi*hi accumulator, slices summed in fp32
+        #    round-to-nearest): 2.1e-6, 2 / 1 flips -- the fp32 kernels' level -- and 0.7 ms less per step
+        #    (scripts/flip_census.py, profiles/r02/flip_census_encoder_predictors*.jsonl).  Clear the two bits for the fp32 kernels.
+        self.tc_mask = (L.TC_DECODER | L.TC_POSTNET | L.TC_DECODER_F8 | L.TC_POSTNET_F8 | L.TC_ENCODER | L.TC_PREDICTORS)
         self._packed = None          # (AcousticModel struct, keep-alive tensors, device)
         self._pos_long = {}          # device position tables longer than max_seq_len, keyed by width
         self._ws = None

@@ -59,7 +59,7 @@ def _e4m3_bytes(x: Tensor) -> Tensor:
     return x.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
 
 
-def pack_conv_tc(w: Tensor, f8: bool = False):
+def pack_conv_tc(w: Tensor, f8: bool = False, nb: int | None = None):
     """[taps][Cin][N] fp32 -> byte buffer for the tcgen05 kernel (see include/fs2b200.h):
          128-byte header (float32[0] = 1/scale, int32[1] = format)  |  [N/NB][Cin/16][taps][2 planes][2 K-chunks][NB][16 bytes]
     Every (tap, 16-channel K-block) stage is one contiguous 64*NB-byte smem image (UMMA no-swizzle K-major).
@@ -68,7 +68,10 @@ def pack_conv_tc(w: Tensor, f8: bool = False):
         K-block's 16 channels -- the B operand of one K = 32 kind::f8f6f4 MMA against the activations' [lo * 2^12 | hi].
     Returns None when the shape is not served by the tensor-core kernel."""
     taps, cin, n = w.shape
-    nb = conv_tc_block(n)
+    if nb is None:
+        nb = conv_tc_block(n)
+    elif n % nb or nb % 16:
+        return None
     if nb == 0 or cin % 16:
         return None
     hi, lo, s = split_fp16(w)
@@ -90,6 +93,25 @@ def pack_conv_tc(w: Tensor, f8: bool = False):
     hb = header.view(torch.uint8).clone()
     hb[4] = 1 if f8 else 0
     return torch.cat([hb, tiles.reshape(-1)])
+
+
+SEG_CIN = 256          # input channels per K-segment of the encoder / predictor path (16 K-steps of the tensor core)
+
+
+def pack_conv_tc_segments(w: Tensor):
+    """[taps][Cin][N] -> taps * (Cin / 256) tile buffers back to back, segment (tap, kc) at index tap * (Cin/256) + kc: a one-tap conv
+    over 256 input channels each, three-MMA split, 64 output channels per work item (FS2_TC_VARIANT_NB64).  Every segment carries
+    its own power-of-two scale header and is 128 + 1024 * N bytes.  None if the shape does not qualify."""
+    taps, cin, n = w.shape
+    if cin % SEG_CIN or n % 64:
+        return None
+    segs = []
+    for tap in range(taps):
+        for kc in range(cin // SEG_CIN):
+            t = pack_conv_tc(w[tap:tap + 1, kc * SEG_CIN:(kc + 1) * SEG_CIN, :].contiguous(), nb=64)
+            assert t is not None and t.numel() == 128 + 1024 * n
+            segs.append(t)
+    return torch.cat(segs)
 
 
 def add_tc_tiles(pk: Dict[str, Tensor], keys, f8_keys=()) -> None:
@@ -138,7 +160,7 @@ def fold_batchnorm(w: Tensor, b: Tensor, gamma: Tensor, beta: Tensor, mean: Tens
 
 
 def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet: int, multi_speaker: bool,
-                  f8_decoder: bool = False, f8_postnet: bool = False) -> Dict[str, Tensor]:
+                  f8_decoder: bool = False, f8_postnet: bool = False, segmented_encoder: bool = True) -> Dict[str, Tensor]:
     pk: Dict[str, Tensor] = {
         "word_emb": g("encoder.src_word_emb.weight").contiguous(),
         "enc_pos": g("encoder.position_enc")[0].contiguous(),
@@ -167,10 +189,16 @@ def pack_acoustic(g: Callable[[str], Tensor], n_enc: int, n_dec: int, n_postnet:
                                 g(p + ".1.running_mean"), g(p + ".1.running_var"))
         pk[f"post.{i}.w"], pk[f"post.{i}.b"] = conv_w(wf), bf.contiguous()
     tc_keys = [f"{side}.{i}.{w}" for side, n in (("enc", n_enc), ("dec", n_dec)) for i in range(n) for w in ("w_qkv", "w_o", "w_1", "w_2")]
-    tc_keys += [f"{nm}.{w}" for nm in ("dur", "pitch", "energy") for w in ("w_c1", "w_c2")]     # predictors: three-MMA split only
+    seg_keys = [k for k in tc_keys if k.startswith("enc.")] + [f"{nm}.{w}" for nm in ("dur", "pitch", "energy") for w in ("w_c1", "w_c2")]
+    tc_keys = [k for k in tc_keys if not k.startswith("enc.")]
     post_keys = ["w_mel"] + [f"post.{i}.w" for i in range(n_postnet)]
     f8 = ([k for k in tc_keys if k.startswith("dec.")] if f8_decoder else []) + (post_keys if f8_postnet else [])
     add_tc_tiles(pk, tc_keys + post_keys, f8)
+    for k in seg_keys:                       # encoder + predictors: K-segmented tiles (fs2_acoustic_model comment in fs2b200.h)
+        w = pk[k]
+        t = pack_conv_tc_segments(w[None] if w.dim() == 2 else w) if segmented_encoder else None
+        if t is not None:
+            pk[k + "_tc"] = t
     return pk
 
 

@@ -53,7 +53,10 @@ enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POS
  * place of the fp16 lo tiles E4M3 tiles [hi * 2^-12 | lo] that one K = 32 kind::f8f6f4 MMA multiplies with the activations'
  * [lo * 2^12 | hi]: y ~ a_hi.w_hi + (a_lo.w_hi + a_hi.w_lo) with the bracket at E4M3 precision (relative error ~2^-16 instead
  * of ~2^-22; 2/3 of the tensor-pipe time and shared-memory operand traffic).  Activations beyond +-448 saturate in the correction. */
-enum { FS2_TC_VARIANT_F8 = 1 };
+enum { FS2_TC_VARIANT_F8 = 1,
+       /* w_tc is tiled for 64 output channels per work item (pack_conv_tc(w, nb=64)): the hi*hi term and the two cross terms then
+        * accumulate in separate tensor-memory tiles.  Used by the K-segmented encoder / predictor path (see fs2_acoustic_model). */
+       FS2_TC_VARIANT_NB64 = 2 };
 
 /* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per work item,
  * s = a per-layer power of two, hi = fp16(s*w), lo = fp16(s*w - hi), the tiled byte buffer is
@@ -102,11 +105,12 @@ typedef struct fs2_conv1d_args {
 } fs2_conv1d_args;
 int fs2_conv1d(const fs2_conv1d_args* a, fs2_stream_t stream);
 
-/* y = LayerNorm_C(x) * gamma + beta over the last dim, then rows t >= row_lens[b] := 0.  x,y contiguous [B][T][C]; C%4==0, C<=1024. */
+/* y = LayerNorm_C(x or relu(x)) * gamma + beta over the last dim, then rows t >= row_lens[b] := 0.  x,y contiguous [B][T][C]; C%4==0, C<=1024. */
 typedef struct fs2_layernorm_args {
   const float* x; float* y; int B, T, C;
   const float* gamma; const float* beta; float eps;
   const int32_t* row_lens; /* [B] or NULL */
+  int pre_relu;            /* 1: LayerNorm(relu(x)) -- the predictors' conv -> ReLU -> LayerNorm (model/modules.py:242-250) when the conv left its ReLU to this op */
 } fs2_layernorm_args;
 int fs2_layernorm(const fs2_layernorm_args* a, fs2_stream_t stream);
 
@@ -220,6 +224,13 @@ typedef struct fs2_predictor_weights {
   const float *w_c1_tc, *w_c2_tc;           /* tensor-core tiles of the two convs (three-MMA split format), or NULL */
 } fs2_predictor_weights;
 
+/* Encoder / predictors on the tensor cores (tc_mask bits FS2_TC_ENCODER / FS2_TC_PREDICTORS): these layers feed the discrete duration and
+ * pitch / energy bucket decisions, where the truncating tensor-core accumulator of a long K loop (432 accumulation steps for the k = 9
+ * conv) costs 5x the error of the fp32 CUDA-core kernel (profiles/r02/flip_census_*.jsonl).  They therefore run K-SEGMENTED: every
+ * (tap, 256-input-channel) slice is its own launch of 16 K-steps whose hi*hi term has its own accumulator (FS2_TC_VARIANT_NB64), and the
+ * slices are summed in fp32 round-to-nearest by the epilogue's accumulate path.  Their w_*_tc pointers then hold
+ * taps * (C_in / 256) tile buffers back to back (segment (tap, kc) at index tap * (C_in/256) + kc, each 128 + 1024 * N bytes:
+ * packing.pack_conv_tc_segments). */
 typedef struct fs2_acoustic_model {
   int d_model, n_head, d_inner, k1, k2, n_enc, n_dec, n_mel;
   int vp_filter, vp_kernel, n_bins, n_vocab, n_speakers;

@@ -21,7 +21,19 @@ for r in data:
     d[r[mi]] = v
 L = list(launch.values())
 ends = [i for i, d in enumerate(L) if "conv_post" in d["name"]]
-step = L[ends[-2] + 1: ends[-1] + 1] if len(ends) >= 2 else L
+starts = [i for i, d in enumerate(L) if "embed_kernel" in d["name"]]
+full = [(a, e) for a in starts for e in ends if a < e and not any(a < x < e for x in starts + ends)]
+if full:                                             # one full step inside the window: embed_kernel ... conv_post_kernel
+    step = L[full[-1][0]: full[-1][1] + 1]
+elif starts and ends and ends[0] < starts[0]:        # window = tail of step A + head of step B (identical steps): stitch one step
+    tail, head = L[: ends[0] + 1], L[starts[0]:]
+    key = [d["name"] for d in tail[:6]]
+    cut = next((i for i in range(len(head)) if [d["name"] for d in head[i:i + 6]] == key and
+                sum("pack_k" in d["name"] for d in head[:i]) + sum("pack_k" in d["name"] for d in tail) ==
+                max(1, sum("pack_k" in d["name"] for d in tail + head) // 2 if sum("pack_k" in d["name"] for d in tail + head) > 6 else 6)), None)
+    step = (head[:cut] + tail) if cut is not None else L
+else:
+    step = L
 tot_us = sum(d.get("gpu__time_duration.sum", 0) for d in step)
 tot_b = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in step)
 tc = [d for d in step if "conv_tc_kernel" in d["name"] or "resstack" in d["name"]]

@@ -134,6 +134,22 @@ def test_fastspeech2_config4_shard_vs_oracle(lj_configs, parity_log):
     _free_running_then_teacher_forced(m, sd, synth.make_batch(64, 128, seed=3), "fs2_config4_shard_B64_L128_vs_oracle", parity_log)
 
 
+@pytest.mark.parametrize("cfg", ["lj", "libri"])
+def test_fastspeech2_tensor_core_encoder_and_predictors(cfg, lj_configs, libri_configs, parity_log):
+    """Both settings of FS2_TC_ENCODER | FS2_TC_PREDICTORS (default: set): encoder FFT blocks and the three variance predictors on tcgen05, K-SEGMENTED (every
+    (tap, 256-channel) slice its own 16-step accumulation, slices summed in fp32 by the epilogue) so that the truncating tensor-core
+    accumulator cannot move the discrete decisions more than the fp32 kernels do.  Same flip-aware protocol as the full-size tests."""
+    from fastspeech2_b200 import _lib as L
+    pc, mc = lj_configs if cfg == "lj" else libri_configs
+    sd = synth.fastspeech2_state_dict(pc, mc, seed=31)
+    batch = synth.make_batch(16, 128, seed=32, n_speakers=904 if cfg == "libri" else 1, min_len=40 if cfg == "libri" else None)
+    for label, bits in (("tc_segmented", L.TC_ENCODER | L.TC_PREDICTORS), ("fp32_cuda_cores", 0)):
+        m = FastSpeech2(pc, mc); m.load_state_dict(sd)
+        m.tc_mask = (m.tc_mask & ~(L.TC_ENCODER | L.TC_PREDICTORS)) | bits
+        m = m.to(DEV).eval()
+        _free_running_then_teacher_forced(m, sd, batch, f"fs2_encoder_predictors_{label}_{cfg}_B16_L128", parity_log)
+
+
 def test_fastspeech2_paper_config_golden(scratch, parity_log):
     """config/LJSpeech_paper (4-layer decoder, frame-level unnormalised pitch / energy, LOG-spaced pitch edges, model/modules.py:48-54)
     against the committed outputs of the unmodified reference (tests/golden/fs2_lj_paper.npz) and the oracle."""
