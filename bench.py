@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--headline-only", action="store_true", help="skip the extra BASELINE.json configs (0, 1, 3, 4-shard)")
     ap.add_argument("--voc-f8-mask", type=int, default=None, help="override hifigan.Generator.f8_mask (A/B of the operand split)")
     ap.add_argument("--voc-fused-mask", type=int, default=None, help="override hifigan.Generator.fused_mask (A/B of the fused ResBlock-group kernel)")
+    ap.add_argument("--voc-pair-mask", type=int, default=None, help="override hifigan.Generator.pair_mask (A/B of the per-pair fused launches)")
     ap.add_argument("--fs2-f8", type=int, default=None, choices=[0, 1], help="override the decoder / PostNet operand split (A/B)")
     return ap.parse_args()
 
@@ -268,6 +269,8 @@ def run_ours(args):
         voc.f8_mask = args.voc_f8_mask
     if args.voc_fused_mask is not None:
         voc.fused_mask = args.voc_fused_mask
+    if args.voc_pair_mask is not None:
+        voc.pair_mask = args.voc_pair_mask
     voc.eval()
     with contextlib.redirect_stdout(io.StringIO()):
         voc.remove_weight_norm()
@@ -501,7 +504,7 @@ def run_ours(args):
                           "algorithmic_tflop_per_step": (fs2_flop_step + HIFIGAN_FLOPS_PER_FRAME * frames_step) / 1e12,
                           "useful_tflops_whole_step": (fs2_flop_step + HIFIGAN_FLOPS_PER_FRAME * frames_step) / (ms_total / args.steps * 1e-3) / 1e12,
                           "configs": extra_cfg,
-                          "operand_split": {"vocoder_f8_mask": int(voc.f8_mask), "vocoder_fused_stage_mask": int(voc.fused_mask),
+                          "operand_split": {"vocoder_f8_mask": int(voc.f8_mask), "vocoder_fused_stage_mask": int(voc.fused_mask), "vocoder_pair_stage_mask": int(voc.pair_mask),
                                             "fs2_tc_mask": int(model.tc_mask)},
                           "build": lib.fs2_build_info().decode()}}
         print(json.dumps(line), flush=True)

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfs2b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LAYERS, MAX_POSTNET, MAX_STAGES, MAX_RESBLOCKS, MAX_DIL = 12, 8, 8, 32, 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
@@ -130,7 +130,7 @@ class VocoderModel(C.Structure):
                 ("w_post", fp), ("b_post", fp),
                 ("w_pre_tc", fp), ("w_up_a_tc", fp * MAX_STAGES), ("w_up_b_tc", fp * MAX_STAGES),
                 ("w_rb1_tc", (fp * MAX_DIL) * MAX_RESBLOCKS), ("w_rb2_tc", (fp * MAX_DIL) * MAX_RESBLOCKS),
-                ("f8_mask", i32), ("fused_mask", i32)]
+                ("f8_mask", i32), ("fused_mask", i32), ("pair_mask", i32), ("pair_kmax", i32)]
 
 
 class ResstackArgs(C.Structure):
@@ -138,7 +138,8 @@ class ResstackArgs(C.Structure):
     _fields_ = [("x", fp), ("y", fp), ("B", i32), ("N", i32), ("C", i32), ("n_kernels", i32), ("n_dil", i32),
                 ("k", i32 * (MAX_DIL + 4)), ("dil", (i32 * MAX_DIL) * (MAX_DIL + 4)),
                 ("w1_tc", (fp * MAX_DIL) * (MAX_DIL + 4)), ("b1", (fp * MAX_DIL) * (MAX_DIL + 4)),
-                ("w2_tc", (fp * MAX_DIL) * (MAX_DIL + 4)), ("b2", (fp * MAX_DIL) * (MAX_DIL + 4))]
+                ("w2_tc", (fp * MAX_DIL) * (MAX_DIL + 4)), ("b2", (fp * MAX_DIL) * (MAX_DIL + 4)),
+                ("alpha", f32), ("accumulate", i32)]
 
 
 class WavInt16Args(C.Structure):

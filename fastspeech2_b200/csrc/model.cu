@@ -428,8 +428,22 @@ static int vocoder_impl(const fs2_vocoder_model* m, const fs2_vocoder_args* a, c
     for (int j = 0; j < m->n_kernels; j++) {
       const int rb = i * m->n_kernels + j, k = m->rb_k[j];
       const float* r = bu;
+      const bool pairs = ((m->pair_mask >> i) & 1) && tcv && (C == 32 || C == 64) && k <= m->pair_kmax;
       for (int d = 0; d < m->n_dil; d++) {
         const int dil = m->rb_dil[j][d];
+        if (pairs) {                                   // one launch per (dilated conv, conv, +x) pair: the intermediate stays on chip
+          const bool lastp = d == m->n_dil - 1;
+          float* dstp = lastp ? bx : (r == r1 ? r2 : r1);
+          fs2_resstack_args ra{};
+          ra.x = r; ra.y = dstp; ra.B = B; ra.N = Ti; ra.C = C; ra.n_kernels = 1; ra.n_dil = 1;
+          ra.k[0] = k; ra.dil[0][0] = dil;
+          ra.w1_tc[0][0] = m->w_rb1_tc[rb][d]; ra.b1[0][0] = m->b_rb1[rb][d];
+          ra.w2_tc[0][0] = m->w_rb2_tc[rb][d]; ra.b2[0][0] = m->b_rb2[rb][d];
+          ra.alpha = lastp ? inv_nk : 1.f; ra.accumulate = lastp && j > 0;
+          FS2_TRY(resstack(&ra, s));
+          r = dstp;
+          continue;
+        }
         FS2_TRY(conv(s, r, B, Ti, C, m->w_rb1[rb][d], m->w_rb1_tc[rb][d], m->b_rb1[rb][d], C, k, dil, (k * dil - dil) / 2, FS2_ACT_LRELU,
                      0.1f, bt, nullptr, FS2_ACT_LRELU, 0.1f, 1.f, 0, nullptr, tcv));
         const bool last = d == m->n_dil - 1;
@@ -452,7 +466,7 @@ using namespace fs2;
 
 extern "C" {
 
-int fs2_abi_version(void) { return 7; }
+int fs2_abi_version(void) { return 8; }
 int fs2_conv_tc_block(int N) { return conv_tc_nb(N); }
 int fs2_conv_tc_plan(const fs2_conv1d_args* a, int num_sms, int32_t* out) { return conv_tc_plan_query(a, num_sms, out); }
 int64_t fs2_kernel_launch_count(void) { return (int64_t)g_launch_count.load(); }

@@ -49,6 +49,7 @@ struct RsP {
   int SB;
   int OBOX, n_oboxes;            // rows per output box (TILE = n_oboxes * OBOX, OBOX % 8 == 0)
   int TPS;                       // conv taps per weight stage (one bulk copy / one handshake)
+  int accumulate;                // the first kernel size reduce-adds into y too
 };
 
 // ------------------------------------------------------------------ TMA (tensor-map) wrappers
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
           for (int hh = 0; hh < NH; hh++)
             for (int bx = 0; bx < p.n_oboxes; bx++) {
               const unsigned char* src = xa + (size_t)(hh * p.n_oboxes + bx) * ((size_t)p.OBOX * 128);
-              if (j == 0) tma_store_3d(&tmy, hh * 32, t0 + bx * p.OBOX, b, src);
+              if (j == 0 && !p.accumulate) tma_store_3d(&tmy, hh * 32, t0 + bx * p.OBOX, b, src);
               else tma_reduce_add_3d(&tmy, hh * 32, t0 + bx * p.OBOX, b, src);
             }
           tma_commit();
@@ -494,11 +495,16 @@ int resstack_plan(const fs2_resstack_args* a, int num_sms, int* out) {
   }
   H = (H + 3) & ~3;                             // TILE = MT*128 - 2H is then a multiple of 8 (whole swizzle atoms per output box)
   const int MT = a->C == 32 ? 4 : 3;            // slab rows = MT*128: bounded by shared memory (two slabs of 4*C bytes per row)
-  const int TILE = MT * 128 - 2 * H;
-  if (TILE < 64) return FS2_ERR_UNSUPPORTED;
-  int obox = 8;                                 // largest divisor of TILE that is a multiple of 8 and a legal TMA box height (<= 256)
-  for (int r = 8; r <= 256; r += 8)
-    if (TILE % r == 0) obox = r;
+  // the result leaves as TMA boxes of `obox` rows (a multiple of 8, <= 256) that tile TILE exactly: widen the halo by up to 32 rows
+  // until TILE splits into at most 12 boxes (e.g. 384 - 2*4 = 376 = 47 x 8 would need 47 stores; 384 - 2*8 = 368 = 2 x 184)
+  int TILE = 0, obox = 0;
+  for (int hc = H; hc <= H + 32 && !obox; hc += 4) {
+    const int tile = MT * 128 - 2 * hc;
+    if (tile < 64) break;
+    for (int r = 256; r >= 8; r -= 8)
+      if (tile % r == 0 && tile / r <= 12) { TILE = tile; obox = r; H = hc; break; }
+  }
+  if (!obox) return FS2_ERR_UNSUPPORTED;
   const long long tiles_per_b = (a->N + TILE - 1) / TILE, items = tiles_per_b * a->B;
   if (items > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   const int TPS = a->C == 32 ? 4 : 2;           // taps per weight stage: 8 KB stages (fewer handshakes per MMA; conv_tc measured -10..-25 %)
@@ -568,7 +574,7 @@ int resstack(const fs2_resstack_args* a, cudaStream_t s) {
       flops += 2.0 * 2.0 * a->B * (double)a->N * a->C * a->C * a->k[j];
     }
   p.H = plan[1]; p.TILE = plan[2]; p.tiles_per_b = (a->N + p.TILE - 1) / p.TILE; p.n_items = plan[3];
-  p.alpha = 1.f / (float)a->n_kernels; p.SB = plan[5]; p.OBOX = plan[8]; p.n_oboxes = plan[9]; p.TPS = plan[10];
+  p.alpha = a->alpha > 0.f ? a->alpha : 1.f / (float)a->n_kernels; p.accumulate = a->accumulate; p.SB = plan[5]; p.OBOX = plan[8]; p.n_oboxes = plan[9]; p.TPS = plan[10];
   alignas(64) CUtensorMap tmx, tmy;
   FS2_TRY(make_map(&tmx, a->x, a->B, a->N, a->C, 128));
   FS2_TRY(make_map(&tmy, a->y, a->B, a->N, a->C, p.OBOX));

@@ -46,6 +46,11 @@ class Generator(nn.Module):
         # 64-channel stage the three-tile slab leaves no room to overlap epilogues with MMAs and the per-layer path is faster
         # (profiles/r02/resstack_*.txt), so it stays opt-in there (fused_mask |= 0b0100).
         self.fused_mask = 0b1000
+        # Stages (bit i) where every (dilated conv, conv, +x) pair with kernel size <= pair_kmax runs as ONE fs2_resstack launch: the
+        # k = 3 / 7 layers of the 64-channel stage move 56-70 % of the HBM peak as single layers (profiles/r02/conv_layer_bench_warm.txt);
+        # fused per pair the intermediate never leaves the SM.
+        self.pair_mask = 0b0100
+        self.pair_kmax = 7
         populate(self, hifigan_spec(self._hd, weight_norm=True))
         with torch.no_grad():  # g = ||v|| so that the initial folded weight equals v, as torch's weight_norm does
             for base in self._bases():
@@ -126,7 +131,8 @@ class Generator(nn.Module):
                 ch //= 2
                 if (int(self.fused_mask) >> i) & 1 and ch in (32, 64):
                     m.fused_mask |= 1 << i
-        m.f8_mask = (int(self.f8_mask) | (m.fused_mask << 1)) if self.use_tensor_cores else 0
+        m.pair_mask, m.pair_kmax = (int(self.pair_mask) & ~m.fused_mask, int(self.pair_kmax)) if self.use_tensor_cores else (0, 0)
+        m.f8_mask = (int(self.f8_mask) | (m.fused_mask << 1) | (m.pair_mask << 1)) if self.use_tensor_cores else 0
         pk = packing.pack_vocoder(lambda b: self._folded(b).float(), lambda b: get(self, b + ".bias").detach().float(),
                                   hd["upsample_rates"], m.n_stages * m.n_kernels, m.n_dil, f8_mask=m.f8_mask)
         P = lambda k: pk[k].data_ptr()

@@ -128,14 +128,15 @@ def conv_post(x, w, bias, in_slope=0.01):
     return wav
 
 
-def resstack(x, kernels, dilations, w1_tc, b1, w2_tc, b2):
+def resstack(x, kernels, dilations, w1_tc, b1, w2_tc, b2, alpha=0.0, out=None, accumulate=False):
     """Fused multi-receptive-field ResBlock group (fs2_resstack).  x [B,N,C] contiguous; kernels [k_j]; dilations [[d...] per j];
     w1_tc / w2_tc [j][d]: pack_conv_tc(w, f8=True) tiles; b1 / b2 [j][d]: biases."""
     _need_cuda(x)
     B, N, Cc = x.shape
     assert x.is_contiguous()
-    y = torch.empty_like(x)
-    a = L.ResstackArgs(x=x.data_ptr(), y=y.data_ptr(), B=B, N=N, C=Cc, n_kernels=len(kernels), n_dil=len(dilations[0]))
+    y = torch.empty_like(x) if out is None else out
+    a = L.ResstackArgs(x=x.data_ptr(), y=y.data_ptr(), B=B, N=N, C=Cc, n_kernels=len(kernels), n_dil=len(dilations[0]),
+                       alpha=float(alpha), accumulate=int(accumulate))
     for j, k in enumerate(kernels):
         a.k[j] = k
         for d, dv in enumerate(dilations[j]):

@@ -184,6 +184,9 @@ typedef struct fs2_resstack_args {
   int k[FS2_MAX_DIL + 4]; int dil[FS2_MAX_DIL + 4][FS2_MAX_DIL];
   const float *w1_tc[FS2_MAX_DIL + 4][FS2_MAX_DIL], *b1[FS2_MAX_DIL + 4][FS2_MAX_DIL];   /* dilated conv of each pair */
   const float *w2_tc[FS2_MAX_DIL + 4][FS2_MAX_DIL], *b2[FS2_MAX_DIL + 4][FS2_MAX_DIL];   /* dilation-1 conv of each pair */
+  float alpha;     /* weight of every kernel size's result; <= 0: 1/n_kernels (the mean) */
+  int accumulate;  /* 1: y += ... (also for the first kernel size) instead of y = ...; with n_kernels = n_dil = 1 the call is ONE fused
+                      conv pair  y (+)= alpha * (conv_k,1(lrelu(conv_k,d(lrelu(x)))) + x)  -- the per-pair mode of the 64-channel stage */
 } fs2_resstack_args;
 int fs2_resstack(const fs2_resstack_args* a, fs2_stream_t stream);
 /* launch plan (pure host logic): out[11] = {128-row tiles per slab, halo rows per side, output rows per work item, work items, grid,
@@ -301,6 +304,9 @@ typedef struct fs2_vocoder_model {
   const float *w_rb1_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL], *w_rb2_tc[FS2_MAX_RESBLOCKS][FS2_MAX_DIL];
   int f8_mask; /* bit 0: w_pre_tc, bit 1+i: every *_tc tile of stage i is in the f16+f8 format (FS2_TC_VARIANT_F8) */
   int fused_mask; /* bit i: the ResBlock group of stage i runs as one fs2_resstack launch (needs f8_mask bit 1+i and 32 / 64 channels) */
+  int pair_mask;  /* bit i: in stage i every (conv_k,d ; conv_k,1 ; +x) pair with k <= pair_kmax runs as one fs2_resstack launch (the
+                     HBM-bound small-kernel layers: the pair's intermediate stays on chip); same requirements as fused_mask */
+  int pair_kmax;
 } fs2_vocoder_model;
 
 typedef struct fs2_vocoder_args {

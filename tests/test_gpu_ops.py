@@ -179,6 +179,27 @@ def test_resstack_fused(case):
     assert err < 3e-4 * max(1.0, want.abs().max().item()), (err, want.abs().max().item())
 
 
+@pytest.mark.parametrize("C,k,dil", [(64, 3, 5), (64, 7, 3), (32, 3, 1)])
+def test_resstack_single_pair_accumulate(C, k, dil):
+    """The per-pair mode of fs2_resstack (n_kernels = n_dil = 1, alpha, accumulate): y += alpha * (conv_k,1(lrelu(conv_k,d(lrelu(x)))) + x)."""
+    import torch.nn.functional as F
+    B, N = 2, 1000
+    x = rnd(B, N, C, seed=41)
+    y0 = rnd(B, N, C, seed=42)
+    wa = rnd(C, C, k, seed=43, scale=0.6 * (C * k) ** -0.5); wb = rnd(C, C, k, seed=44, scale=0.6 * (C * k) ** -0.5)
+    ba, bb = rnd(C, seed=45, scale=0.05), rnd(C, seed=46, scale=0.05)
+    r = x.double().transpose(1, 2)
+    t = F.conv1d(F.leaky_relu(r, 0.1), wa.double(), ba.double(), dilation=dil, padding=(k - 1) * dil // 2)
+    t = F.conv1d(F.leaky_relu(t, 0.1), wb.double(), bb.double(), padding=(k - 1) // 2)
+    want = y0.double() + (1.0 / 3) * (t + r).transpose(1, 2)
+    out = y0.to(DEV).clone()
+    ops.resstack(x.to(DEV), (k,), ((dil,),), [[packing.pack_conv_tc(packing.conv_w(wa), f8=True).to(DEV)]], [[ba.to(DEV)]],
+                 [[packing.pack_conv_tc(packing.conv_w(wb), f8=True).to(DEV)]], [[bb.to(DEV)]], alpha=1.0 / 3, out=out, accumulate=True)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - want).abs().max().item()
+    assert err < 1e-4 * max(1.0, want.abs().max().item()), err
+
+
 def test_conv1d_tensor_core_alignment_contract():
     """The tcgen05 kernel reads activations with 256-bit loads: a 16-byte-but-not-32-byte aligned x is refused by the explicit
     backend and silently served by the exact fp32 kernel under FS2_CONV_AUTO (same contract, fp32 accuracy)."""
