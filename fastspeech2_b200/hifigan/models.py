@@ -47,10 +47,12 @@ class Generator(nn.Module):
         # (profiles/r02/resstack_*.txt), so it stays opt-in there (fused_mask |= 0b0100).
         self.fused_mask = 0b1000
         # Stages (bit i) where every (dilated conv, conv, +x) pair with kernel size <= pair_kmax runs as ONE fs2_resstack launch: the
-        # k = 3 / 7 layers of the 64-channel stage move 56-70 % of the HBM peak as single layers (profiles/r02/conv_layer_bench_warm.txt);
-        # fused per pair the intermediate never leaves the SM.
+        # k = 3 layers of the 64-channel stage move 0.7 of the HBM peak as single layers (profiles/r02/conv_layer_bench_warm.txt);
+        # fused per pair the intermediate never leaves the SM.  Measured per pair (profiles/r02/pair_bench.txt): k = 3 556 vs 587 us
+        # for the two launches, but k = 7 842-902 vs 665 and k = 11 1133-1264 vs 801 -- one item in flight per SM serialises the
+        # pair's MMAs and epilogues, which only the HBM-bound k = 3 pairs can afford -- hence pair_kmax = 3.
         self.pair_mask = 0b0100
-        self.pair_kmax = 7
+        self.pair_kmax = 3
         populate(self, hifigan_spec(self._hd, weight_norm=True))
         with torch.no_grad():  # g = ||v|| so that the initial folded weight equals v, as torch's weight_norm does
             for base in self._bases():
