@@ -20,6 +20,7 @@ TC_DECODER_F8, TC_POSTNET_F8 = 16, 32
 TC_ATTENTION_GEMM = 64
 TC_VARIANT_F8 = 1
 TC_VARIANT_NB64 = 2
+TC_VARIANT_SEGMENTED = 4
 PROF_CLASSES = 5
 
 fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())

@@ -42,9 +42,8 @@ __device__ __forceinline__ void split8(const float (&f)[8], float scale, uint4& 
 }
 
 // K tiles: GEMM weights W[c = d][n = key], layout  header | [key/128][d/16][hi|lo][2 chunks][128 keys][8 halfs]
-__global__ void pack_k_tiles_kernel(const float* __restrict__ qkv, unsigned char* __restrict__ tiles, int B, int T, int Tk, int H,
-                                    long long tile_stride) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (bh, key, dchunk)
+__device__ __forceinline__ void pack_k_tiles(const float* __restrict__ qkv, unsigned char* __restrict__ tiles, int B, int T, int Tk, int H,
+                                             long long tile_stride, long long idx) {   // idx = (bh, key, dchunk)
   const long long total = (long long)B * H * Tk * (AT_DH / 8);
   if (idx >= total) return;
   const int dchunk = (int)(idx % (AT_DH / 8));
@@ -73,9 +72,8 @@ __global__ void pack_k_tiles_kernel(const float* __restrict__ qkv, unsigned char
 }
 
 // V tiles: GEMM weights W[c = key][n = d], layout  header | [key/16][hi|lo][2 chunks of 8 keys][128 d][8 halfs (keys)]
-__global__ void pack_v_tiles_kernel(const float* __restrict__ qkv, unsigned char* __restrict__ tiles, int B, int T, int Tk, int H,
-                                    long long tile_stride) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (bh, key8, d)
+__device__ __forceinline__ void pack_v_tiles(const float* __restrict__ qkv, unsigned char* __restrict__ tiles, int B, int T, int Tk, int H,
+                                             long long tile_stride, long long idx) {   // idx = (bh, key8, d)
   const long long total = (long long)B * H * (Tk / 8) * AT_DH;
   if (idx >= total) return;
   const int d = (int)(idx % AT_DH);
@@ -99,6 +97,13 @@ __global__ void pack_v_tiles_kernel(const float* __restrict__ qkv, unsigned char
   unsigned char* dst = base + AT_HDR + (size_t)kb * stage + ((size_t)chunk * AT_NB + d) * 16;
   *reinterpret_cast<uint4*>(dst) = hi;
   *reinterpret_cast<uint4*>(dst + b_plane) = lo;
+}
+
+// One launch writes both operand-tile sets: blocks [0, k_blocks) the K tiles, the rest the V tiles.
+__global__ void pack_kv_tiles_kernel(const float* __restrict__ qkv, unsigned char* __restrict__ kt, unsigned char* __restrict__ vt, int B, int T,
+                                     int Tk, int H, long long tile_stride, unsigned k_blocks) {
+  if (blockIdx.x < k_blocks) pack_k_tiles(qkv, kt, B, T, Tk, H, tile_stride, (long long)blockIdx.x * blockDim.x + threadIdx.x);
+  else pack_v_tiles(qkv, vt, B, T, Tk, H, tile_stride, (long long)(blockIdx.x - k_blocks) * blockDim.x + threadIdx.x);
 }
 
 // In-place row softmax of S [B*H][T][Tk] with scale and key-padding mask; one warp per row, row held in registers.
@@ -156,11 +161,10 @@ int pack_kv_tiles(const fs2_attention_args* a, unsigned char* kt, unsigned char*
   const int B = a->B, T = a->T, H = a->H;
   const int Tk = (T + 127) / 128 * 128;
   const long long nk = (long long)B * H * Tk * (AT_DH / 8), nv = (long long)B * H * (Tk / 8) * AT_DH;
+  const unsigned kb = (unsigned)((nk + 255) / 256), vb = (unsigned)((nv + 255) / 256);
   prof_before(s);
-  pack_k_tiles_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(a->qkv, kt, B, T, Tk, H, tstride);
-  pack_v_tiles_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(a->qkv, vt, B, T, Tk, H, tstride);
+  pack_kv_tiles_kernel<<<kb + vb, 256, 0, s>>>(a->qkv, kt, vt, B, T, Tk, H, tstride, kb);
   prof_after(s, 1, 0.0);
-  g_launch_count++;
   FS2_LAUNCH_CHECK();
   return FS2_OK;
 }

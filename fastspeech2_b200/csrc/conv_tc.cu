@@ -130,6 +130,18 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->taps <= 0) return FS2_ERR_ARG;
   if (!conv_tc_supported(a)) return FS2_ERR_UNSUPPORTED;
   if (!aligned16(a->x) || !aligned16(wt) || !aligned16(a->y) || (a->res && !aligned16(a->res))) return FS2_ERR_ARG;
+  // K-segmented evaluation in ONE launch (FS2_TC_VARIANT_SEGMENTED): the work units are (tile, tap, 256-channel chunk)
+  fs2_conv1d_args seg_args;
+  int nseg = 1, seg_nkc = 1;
+  if (variant & FS2_TC_VARIANT_SEGMENTED) {
+    if (!(variant & FS2_TC_VARIANT_NB64) || a->Cin % 256 || a->N % 64 || a->dilation != 1 || a->alpha != 1.f || a->out_act != FS2_ACT_NONE ||
+        wt_batch_stride != 0)
+      return FS2_ERR_UNSUPPORTED;
+    seg_nkc = a->Cin / 256; nseg = a->taps * seg_nkc;
+    seg_args = *a;
+    seg_args.Cin = 256; seg_args.taps = 1;          // shape of one slice: ring / tile planning happens on this
+  }
+  const fs2_conv1d_args* plan_args = nseg > 1 || (variant & FS2_TC_VARIANT_SEGMENTED) ? &seg_args : a;
   int derr = FS2_OK;
   DevState* dv = dev_state(&derr);                      // state of the CURRENT device: the caller's stream must belong to it
   if (!dv) return derr;
@@ -147,9 +159,10 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   const int g_num_sms = dv->num_sms.load(std::memory_order_relaxed);
   TcP p{};
   p.x = a->x; p.xbs = a->x_batch_stride; p.xrs = a->x_row_stride;
-  p.B = a->B; p.T = a->T; p.Cin = a->Cin;
+  p.B = a->B; p.T = a->T; p.Cin = plan_args->Cin;
   p.wt = wt; p.wt_bstride = wt_batch_stride; p.bias = a->bias; p.N = a->N;
-  p.taps = a->taps; p.dil = a->dilation; p.pad = a->pad_left;
+  p.taps = plan_args->taps; p.dil = a->dilation; p.pad = a->pad_left;
+  p.nseg = nseg; p.seg_nkc = seg_nkc; p.seg_wbytes = TC_HDR + (long long)1024 * a->N;
   p.in_act = a->in_act; p.in_slope = a->in_slope; p.out_act = a->out_act; p.out_slope = a->out_slope;
   p.res = a->res; p.rbs = a->res_batch_stride; p.rrs = a->res_row_stride;
   p.alpha = a->alpha; p.accumulate = a->accumulate; p.row_lens = a->row_lens;
@@ -159,7 +172,7 @@ int conv1d_tc(const fs2_conv1d_args* a, const float* wt, unsigned variant, cudaS
   p.f8 = (variant & FS2_TC_VARIANT_F8) ? 1 : 0;
   size_t smem = 0;
   int grid = 0;
-  const int rc = conv_tc_plan(a, g_num_sms, p, smem, grid);
+  const int rc = conv_tc_plan(plan_args, g_num_sms, p, smem, grid);
   if (rc != FS2_OK) return rc;
   const int mt = p.MT;
   prof_before(s);

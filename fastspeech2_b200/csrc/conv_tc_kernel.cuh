@@ -74,6 +74,11 @@ struct TcP {
   long long* trace;                // debug: [CTA][16 items][8] globaltimer stamps, or NULL
   unsigned variant;                // reserved for A/B experiments (unused by the shipped kernel)
   int pdl;                         // launched with programmatic stream serialisation: wait for the previous grid before touching its data
+  int nseg;                        // K-segments per output tile (1 = plain conv).  > 1: the conv is the sum of nseg one-tap slices over p.Cin (= 256)
+                                   // input channels each, slice s = (tap = s / seg_nkc, channel chunk = s % seg_nkc); every slice is its own work unit with a
+                                   // fresh accumulator, and the units of one tile run back to back on one CTA, adding into y in fp32 (FS2_TC_VARIANT_SEGMENTED)
+  int seg_nkc;                     // channel chunks per tap
+  long long seg_wbytes;            // bytes between the tile buffers of consecutive slices
   int f8;                          // operand split: 0 = three kind::f16 MMAs (hi*hi + lo*hi + hi*lo), 1 = kind::f16 main term + ONE kind::f8f6f4 correction MMA
 };
 
@@ -458,7 +463,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       int nblk = (int)blockIdx.x / per_blk, rem = (int)blockIdx.x - nblk * per_blk;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const long long wb = p.wt_bstride ? (long long)(rem / p.tiles_per_batch) * p.wt_bstride : 0;
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + wb + TC_HDR + (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
+        for (int seg = 0; seg < p.nseg; seg++) {
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wt) + (long long)seg * p.seg_wbytes + wb + TC_HDR +
+                                    (size_t)nblk * p.taps * KBLOCKS * stage_bytes;
         const unsigned char* src = wsrc;           // tiles are ordered [kb][tap]: the taps of one K-block are contiguous
         for (int kb = 0; kb < KBLOCKS; kb++) {
           for (int tap = 0; tap < p.taps; tap += p.TPS) {
@@ -470,6 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
             src += bytes;
             rb.advance(SB);
           }
+        }
         }
         rem += (int)gridDim.x;
         while (rem >= per_blk) { rem -= per_blk; nblk++; }
@@ -489,7 +497,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const uint32_t g_cross = TG >= 2 ? (uint32_t)p.acc_stride : 0u;            // lo*hi and hi*lo
     Ring ra, rb, rt;
     uint32_t itT = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x)
+    for (int seg = 0; seg < p.nseg; seg++, itT++, rt.advance(2)) {           // one work unit per (item, K-segment)
       const uint32_t buf = rt.idx;
       mbar_wait(&accEmpty[buf], rt.phase ^ 1);                    // epilogue has drained this accumulator set
       tc_fence_after();
@@ -573,15 +582,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       goff[u] = (idx >> 1) * (int)p.xrs + (idx & 1) * 8;              // global float offset from the slab's first row
     }
     // load cursor (runs TC_DEPTH K-blocks ahead of the store cursor); no divisions on the per-K-block path
-    int l_item = blockIdx.x, l_kb = 0;
+    int l_item = blockIdx.x, l_kb = 0, l_seg = 0;
     const float* l_xrow = nullptr;                     // &x[b][t0 - pad][0]; rows outside [0, T) are never dereferenced
     int l_tfirst = 0;
     bool l_interior = false;                           // warp-uniform: every slab row of the item exists
     auto l_set_item = [&]() {
       if (l_item < p.n_items) {
         const Item it = decode_item(p, l_item);
-        l_tfirst = it.t0 - p.pad;
-        l_xrow = p.x + (long long)it.b * p.xbs + (long long)l_tfirst * p.xrs;
+        const int s_tap = l_seg / p.seg_nkc, s_kc = l_seg - s_tap * p.seg_nkc;   // K-segment: one tap, one 256-channel chunk (0, 0 when nseg == 1)
+        l_tfirst = it.t0 - p.pad + s_tap;
+        l_xrow = p.x + (long long)it.b * p.xbs + (long long)l_tfirst * p.xrs + s_kc * p.Cin;
         l_interior = l_tfirst >= 0 && l_tfirst + rows_needed <= p.T;
       }
     };
@@ -604,10 +614,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
           }
         }
       }
-      if (++l_kb == KBLOCKS) { l_kb = 0; l_item += gridDim.x; l_set_item(); }
+      if (++l_kb == KBLOCKS) {
+        l_kb = 0;
+        if (++l_seg == p.nseg) { l_seg = 0; l_item += gridDim.x; }
+        l_set_item();
+      }
     };
     const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total = my_items * KBLOCKS;
+    const int total = my_items * p.nseg * KBLOCKS;
 #pragma unroll
     for (int d = 0; d < DEPTH; d++)
       if (d < total) issue_loads(v[d]);
@@ -651,6 +665,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
     const float inv_ws = __ldg(p.wt);                  // header: 1 / (power-of-two weight scale); identical for every utterance
     uint32_t itT = 0;
     Ring rt;
+    if (p.nseg == 1) {
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, itT++, rt.advance(2)) {
       const uint32_t buf = rt.idx;
       const Item it = decode_item(p, item);
@@ -668,6 +683,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcP p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&accEmpty[buf]);      // this warp's tcgen05.ld of the set have completed
       if (warp == 2 + TC_TW && lane == 0) TC_STAMP((int)itT, 5);
+    }
+    } else {
+      // K-segmented conv: unit (item, seg) adds slice seg of the tile into y -- bias with the first slice; residual, alpha-free sum and
+      // the pad-row mask with the last.  The units of one tile run back to back on this CTA and every thread re-reads what it wrote,
+      // so the fp32 read-modify-write of y needs no further ordering.  No output activation (checked on the host).
+      TcP u = p;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        for (int seg = 0; seg < p.nseg; seg++, itT++, rt.advance(2)) {
+          const uint32_t buf = rt.idx;
+          const bool first = seg == 0, last = seg == p.nseg - 1;
+          u.bias = first ? p.bias : nullptr;
+          u.res = last ? p.res : nullptr;
+          u.row_lens = last ? p.row_lens : nullptr;
+          u.accumulate = (!first || p.accumulate) ? 1 : 0;
+          const float seg_inv_ws = __ldg(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p.wt) + (long long)seg * p.seg_wbytes));
+          mbar_wait(&accFull[buf], rt.phase);
+          tc_fence_after();
+          tc_epilogue_dispatch<FS2_ACT_NONE>(u, tmem + buf * acc_set, stage, q, lane, it, seg_inv_ws);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&accEmpty[buf]);
+        }
+      }
     }
   }
 

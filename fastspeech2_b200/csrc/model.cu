@@ -130,37 +130,24 @@ static int ln(cudaStream_t s, const float* x, float* y, int B, int T, int C, con
 }
 
 // K-segmented tensor-core convolution for the layers that feed the discrete decisions (encoder, predictors): the sum over taps and
-// input channels is cut into (tap, 256-channel) slices; each slice is one tcgen05 launch of 16 K-steps with separate accumulators for
-// the hi*hi term and the cross terms (FS2_TC_VARIANT_NB64), and the slices are added in fp32 round-to-nearest by the epilogue's
-// accumulate path.  That bounds the tensor core's truncating accumulation to 16 steps per chain (a single k = 9 launch has 432) and
+// input channels is cut into (tap, 256-channel) slices; each slice is one work unit of 16 K-steps with separate accumulators for
+// the hi*hi term and the cross terms (FS2_TC_VARIANT_NB64 | FS2_TC_VARIANT_SEGMENTED, one launch per conv), and the slices are added in
+// fp32 round-to-nearest by the epilogue's accumulate path.  That bounds the tensor core's truncating accumulation to 16 steps per chain (a single k = 9 launch has 432) and
 // brings the error back to the fp32 CUDA-core kernel's level (profiles/r02/flip_census_*.jsonl).  `w_seg`: taps * (Cin/256) tile
 // buffers of 128 + 1024*N bytes (packing.pack_conv_tc_segments).  y = bias + sum_slices + res, rows >= row_lens zeroed; no output
 // activation (a following ReLU is applied by the consumer: in_act of the next conv / pre_relu of the LayerNorm).
 static int conv_seg(cudaStream_t s, const float* x, int B, int T, int Cin, const float* w_seg, const float* bias, int N, int taps, int pad,
                     float* y, const float* res, int in_act, float in_slope, const int32_t* row_lens) {
-  constexpr int SEG = 256;
-  if (Cin % SEG || N % 64) return FS2_ERR_UNSUPPORTED;
-  const int nkc = Cin / SEG, nseg = taps * nkc;
-  const size_t seg_bytes = 128 + (size_t)1024 * N;
-  for (int tap = 0; tap < taps; tap++)
-    for (int kc = 0; kc < nkc; kc++) {
-      const int idx = tap * nkc + kc;
-      fs2_conv1d_args a{};
-      a.x = x + kc * SEG; a.x_batch_stride = (int64_t)T * Cin; a.x_row_stride = Cin;
-      a.B = B; a.T = T; a.Cin = SEG;
-      a.w = nullptr; a.w_tc = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(w_seg) + idx * seg_bytes);
-      a.backend = FS2_CONV_TC; a.tc_variant = FS2_TC_VARIANT_NB64;
-      a.bias = idx == 0 ? bias : nullptr;
-      a.N = N; a.taps = 1; a.dilation = 1; a.pad_left = pad - tap;
-      a.in_act = in_act; a.in_slope = in_slope; a.out_act = FS2_ACT_NONE;
-      const bool last = idx == nseg - 1;
-      a.res = last ? res : nullptr; a.res_batch_stride = (int64_t)T * N; a.res_row_stride = N;
-      a.alpha = 1.f; a.accumulate = idx > 0;
-      a.row_lens = last ? row_lens : nullptr;
-      a.y = y; a.y_batch_stride = (int64_t)T * N; a.y_row_stride = N;
-      FS2_TRY(conv1d_tc(&a, a.w_tc, a.tc_variant, s));
-    }
-  return FS2_OK;
+  fs2_conv1d_args a{};
+  a.x = x; a.x_batch_stride = (int64_t)T * Cin; a.x_row_stride = Cin;
+  a.B = B; a.T = T; a.Cin = Cin;
+  a.w = nullptr; a.w_tc = w_seg; a.backend = FS2_CONV_TC; a.tc_variant = FS2_TC_VARIANT_NB64 | FS2_TC_VARIANT_SEGMENTED;
+  a.bias = bias; a.N = N; a.taps = taps; a.dilation = 1; a.pad_left = pad;
+  a.in_act = in_act; a.in_slope = in_slope; a.out_act = FS2_ACT_NONE;
+  a.res = res; a.res_batch_stride = (int64_t)T * N; a.res_row_stride = N;
+  a.alpha = 1.f; a.accumulate = 0; a.row_lens = row_lens;
+  a.y = y; a.y_batch_stride = (int64_t)T * N; a.y_row_stride = N;
+  return conv1d_tc(&a, a.w_tc, a.tc_variant, s);
 }
 
 struct FftBufs { float *x, *tmp, *qkv, *ctx, *hid; void* att_ws; size_t att_bytes; };

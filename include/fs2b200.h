@@ -56,7 +56,12 @@ enum { FS2_TC_ENCODER = 1, FS2_TC_PREDICTORS = 2, FS2_TC_DECODER = 4, FS2_TC_POS
 enum { FS2_TC_VARIANT_F8 = 1,
        /* w_tc is tiled for 64 output channels per work item (pack_conv_tc(w, nb=64)): the hi*hi term and the two cross terms then
         * accumulate in separate tensor-memory tiles.  Used by the K-segmented encoder / predictor path (see fs2_acoustic_model). */
-       FS2_TC_VARIANT_NB64 = 2 };
+       FS2_TC_VARIANT_NB64 = 2,
+       /* with NB64: w_tc holds taps * (C_in / 256) one-tap tile buffers back to back (packing.pack_conv_tc_segments) and the conv is
+        * evaluated K-SEGMENTED inside one launch: every (tile, tap, 256-channel chunk) is a work unit with a fresh 16-step accumulator,
+        * the units of a tile run back to back on one CTA and add into y in fp32 round-to-nearest (bias with the first, residual and
+        * pad-row mask with the last).  Needs dilation 1, alpha 1, no output activation, C_in % 256 == 0, N % 64 == 0. */
+       FS2_TC_VARIANT_SEGMENTED = 4 };
 
 /* Tensor-core weight tiles.  For a conv weight w[taps][Cin][N] with NB = fs2_conv_tc_block(N) output channels per work item,
  * s = a per-layer power of two, hi = fp16(s*w), lo = fp16(s*w - hi), the tiled byte buffer is

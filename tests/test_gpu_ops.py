@@ -137,6 +137,40 @@ def test_conv1d_tensor_core_f8_split(case):
     assert err_exact < 1.5e-3, (err_contract, err_exact)       # ~2^-16 relative on O(1..10) outputs (single-pass fp16: ~2e-2 here)
 
 
+SEG_CASES = [
+    # B, T, Cin, N, taps, pad, in_act (0 none / 3 = lrelu slope 0 = ReLU), res, lens
+    (2, 128, 256, 768, 1, 0, 0, False, False),      # encoder QKV projection
+    (3, 100, 256, 1024, 9, 4, 0, False, False),     # conv-FFN w_1 (pre-activation output)
+    (2, 128, 1024, 256, 1, 0, 3, True, True),       # conv-FFN w_2: ReLU on the input, residual, pad-row mask, 4 channel chunks
+    (2, 300, 256, 256, 3, 1, 0, False, False),      # predictor conv, T > 256 (several tiles per utterance)
+]
+
+
+@pytest.mark.parametrize("case", SEG_CASES)
+def test_conv1d_tensor_core_k_segmented(case):
+    """FS2_TC_VARIANT_NB64 | FS2_TC_VARIANT_SEGMENTED: one launch whose work units are (tile, tap, 256-channel chunk) slices with fresh
+    16-step accumulators, summed in fp32 through y.  Against the fp64 contract the error must be at the fp32 kernel's level (the point
+    of the segmentation: a single 432-step accumulation leaves 5x more)."""
+    B, T, Cin, N, taps, pad, in_act, use_res, use_lens = case
+    x = rnd(B, T, Cin, seed=1)
+    w = rnd(taps, Cin, N, seed=2, scale=(taps * Cin) ** -0.5)
+    bias = rnd(N, seed=3, scale=0.1)
+    res = rnd(B, T, N, seed=4) if use_res else None
+    lens = torch.tensor([max(1, T - 7 * (i + 1)) for i in range(B)], dtype=torch.int32) if use_lens else None
+    d = lambda t: None if t is None else t.double()
+    want = E.conv1d(x.double(), w.double(), bias.double(), 1, pad, in_act, 0.0, 0, 0.0, d(res), 1.0, None, lens)
+    wseg = packing.pack_conv_tc_segments(w)
+    assert wseg is not None and wseg.numel() == taps * (Cin // 256) * (128 + 1024 * N)
+    got = ops.conv1d(x.to(DEV), w.to(DEV), bias.to(DEV), pad_left=pad, in_act=in_act, in_slope=0.0, res=None if res is None else res.to(DEV),
+                     row_lens=None if lens is None else lens.to(DEV), w_tc=wseg.to(DEV), backend=2, tc_variant=2 | 4)
+    exact = ops.conv1d(x.to(DEV), w.to(DEV), bias.to(DEV), pad_left=pad, in_act=in_act, in_slope=0.0, res=None if res is None else res.to(DEV),
+                       row_lens=None if lens is None else lens.to(DEV), backend=1)
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - want).abs().max().item()
+    err_fp32 = (exact.cpu().double() - want).abs().max().item()
+    assert err < 4e-6 and err < 4 * err_fp32 + 1e-6, (err, err_fp32)
+
+
 RESSTACK_CASES = [
     # B, N, C, kernels, dilations
     (1, 700, 32, (3, 7, 11), ((1, 3, 5),) * 3),       # two work items, ragged second tile
