@@ -11,6 +11,7 @@ BASELINE.json configs[2]; the mel-only configs[1] number is reported in `extra`.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -33,6 +34,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warm-seconds", type=float, default=1.0, help="minimum wall time of the untimed warm-up (steps are added to --warmup until it is reached)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step")
     ap.add_argument("--phonemes", type=int, default=128)
@@ -42,6 +44,7 @@ def parse():
     ap.add_argument("--headline-only", action="store_true", help="skip the extra BASELINE.json configs (0, 1, 3, 4-shard)")
     ap.add_argument("--voc-f8-mask", type=int, default=None, help="override hifigan.Generator.f8_mask (A/B of the operand split)")
     ap.add_argument("--voc-fused-mask", type=int, default=None, help="override hifigan.Generator.fused_mask (A/B of the fused ResBlock-group kernel)")
+    ap.add_argument("--voc-pair-kmax", type=int, default=None, help="override hifigan.Generator.pair_kmax (largest kernel size run as fused pairs)")
     ap.add_argument("--voc-pair-mask", type=int, default=None, help="override hifigan.Generator.pair_mask (A/B of the per-pair fused launches)")
     ap.add_argument("--fs2-f8", type=int, default=None, choices=[0, 1], help="override the decoder / PostNet operand split (A/B)")
     return ap.parse_args()
@@ -140,7 +143,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "sampler": self.mode}
         busy = [c for c, w in zip(sm, pw) if w > 250.0] or sm          # samples taken under load (idle draw is ~150 W)
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "samples_under_load": len(busy),
+        return {"sm_mhz": statistics.median(busy), "sm_mhz_min": min(busy), "sm_mhz_last_samples": busy[-4:], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "samples_under_load": len(busy),
                 "reasons": sorted(reasons), "sampler": self.mode}
 
 
@@ -271,6 +274,8 @@ def run_ours(args):
         voc.fused_mask = args.voc_fused_mask
     if args.voc_pair_mask is not None:
         voc.pair_mask = args.voc_pair_mask
+    if args.voc_pair_kmax is not None:
+        voc.pair_kmax = args.voc_pair_kmax
     voc.eval()
     with contextlib.redirect_stdout(io.StringIO()):
         voc.remove_weight_norm()
@@ -288,14 +293,24 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = lib.fs2_kernel_launch_count()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]      # one event record per step: the per-step spread, for diagnosis
+        gc_was = gc.isenabled()
+        gc.collect()
+        gc.disable()                             # (as timeit does) no cyclic-GC pause on the launching thread inside the timed region
         e0.record()
         last = None
-        for _ in range(steps):
+        for i in range(steps):
             last = fn()
+            marks[i].record()
         e1.record()
         torch.cuda.synchronize()
+        if gc_was:
+            gc.enable()
         if world > 1 and collective:
             dist.barrier()
+        each = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        per = sorted(each)
+        timed.spread = {"min": round(per[0], 3), "median": round(per[len(per) // 2], 3), "max": round(per[-1], 3), "slowest_step_index": each.index(per[-1])}
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         launches = torch.tensor([lib.fs2_kernel_launch_count() - n0], device=dev, dtype=torch.int64)
         if world > 1 and collective:
@@ -351,7 +366,7 @@ def run_ours(args):
         out, wav = step_device()
         torch.cuda.synchronize()
     dt = time.perf_counter() - t_w0
-    extra = torch.tensor([min(200, max(0, int((1.0 - dt) / max(dt / (warm_steps - 1), 1e-4)) + 1)) if dt < 1.0 else 0], device=dev)
+    extra = torch.tensor([min(200, max(0, int((args.warm_seconds - dt) / max(dt / (warm_steps - 1), 1e-4)) + 1)) if dt < args.warm_seconds else 0], device=dev)
     if world > 1:                                     # every rank runs the same number of (collective-carrying) steps
         dist.all_reduce(extra, op=dist.ReduceOp.MAX)
     for _ in range(int(extra.item())):
@@ -367,6 +382,7 @@ def run_ours(args):
     # N > 1: the asynchronous gather of the last step completes inside the timed region (flush before the closing event)
     ms_total, launches, _ = timed(step_device, args.steps) if gather is None else _timed_with_flush(timed, step_device, gather, args.steps)
     clocks = sampler.stop() if sampler else None
+    spread_device = dict(timed.spread)
     value = samples_step * args.steps / (ms_total * 1e-3)
 
     ms_mel, _, _ = timed(lambda: model(spk, texts, lens, L), args.steps)
@@ -376,6 +392,7 @@ def run_ours(args):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps) if gather is None else _timed_with_flush(timed, step_e2e, gather, args.steps)
     e2e_value = samples_step * args.steps / (ms_e2e * 1e-3)
+    spread_e2e = dict(timed.spread)
     h2d = spk_h.numel() * 8 + texts_h.numel() * 8 + lens_h.numel() * 8
     d2h = int(wav.numel() * 4 + out[9].numel() * 8)
 
@@ -499,7 +516,8 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,
                 "roofline": roof, "cpu_baseline": cpu,
-                "extra": {"mel_frames_per_s": frames_step * args.steps / (ms_total * 1e-3),
+                "extra": {"step_ms_spread": {"device_timed": spread_device, "e2e": spread_e2e, "note": "this rank's per-step CUDA-event durations"},
+                          "mel_frames_per_s": frames_step * args.steps / (ms_total * 1e-3),
                           "fastspeech2_only_mel_frames_per_s": mel_fps, "fastspeech2_only_ms_per_step": ms_mel / args.steps,
                           "algorithmic_tflop_per_step": (fs2_flop_step + HIFIGAN_FLOPS_PER_FRAME * frames_step) / 1e12,
                           "useful_tflops_whole_step": (fs2_flop_step + HIFIGAN_FLOPS_PER_FRAME * frames_step) / (ms_total / args.steps * 1e-3) / 1e12,

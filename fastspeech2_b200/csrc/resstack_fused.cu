@@ -118,7 +118,12 @@ __device__ __forceinline__ void rs_store16(unsigned char* kblk, uint32_t chunk_b
 
 __device__ __forceinline__ float rs_lrelu(float v) { return fmaxf(v, 0.1f * v); }   // LRELU_SLOPE = 0.1 (hifigan/models.py:7)
 
-template <int C, int MT>
+// INDEP = false: the MT tiles form one contiguous slab (halo at its two ends only): whole ResBlock groups.
+// INDEP = true : every 128-row tile is its own mini-slab with its own H-row halo (VT = 128 - 2H output rows per tile): single conv pairs, where
+//                H is small.  The tiles of a work item are then independent, so the two MMA groups ping-pong with the row warps without
+//                any cross-group wait; the result is staged in a buffer of its own and the next item's input boxes are prefetched into XT
+//                as soon as the last conv's MMAs have retired, so the TMA latencies overlap the epilogue instead of the next item's start.
+template <int C, int MT, bool INDEP>
 __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                                                                  const RsP p) {
   // one row warp per (TMEM lane quarter, 16-channel column group): 8 warps for 32 channels, 16 for 64 -- the epilogue is the
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
   constexpr int NH = C / 32;                                           // 32-channel (128-byte) column blocks of a row
   // tiles in the first MMA group.  The next conv's first group needs the epilogues of tiles 0 .. G0N: with a 3-tile slab {0} | {1,2}
   // lets it start after ONE tile's epilogue beyond the MMAs ({0,1} | {2} needed all three); with 4 tiles {0,1} | {2,3}.
-  constexpr int G0N = MT == 3 ? 1 : 2;
+  constexpr int G0N = INDEP ? MT / 2 : (MT == 3 ? 1 : 2);
   // Alternative kept for experiments: with 32 channels a whole conv's weight stages fit in the ring, so they can be streamed ONCE and
   // the MMAs issued tile by tile (tile m of the next conv starts as soon as tiles m-1 .. m+1 are through their epilogue).  Measured
   // slower than the two-group schedule (6.43 vs 5.67 ms on the 32-channel stage, profiles/r02/resstack_bench_*.txt): the single
@@ -143,7 +148,9 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
   unsigned char* smem0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms are 1024 bytes
   unsigned char* xa = smem0 + RS_GUARD;          // 1024-byte aligned: doubles as the swizzled staging area of the result
   unsigned char* xt = xa + SLAB;                 //                    doubles as the landing area of the fp32 input boxes
-  unsigned char* ring = xt + SLAB;
+  unsigned char* stg = xt + SLAB;                // INDEP: staging area of the result boxes (otherwise XA is used)
+  unsigned char* ring = INDEP ? stg + SLAB : xt + SLAB;
+  const int VT = 128 - 2 * p.H;                  // INDEP: output rows per tile
   const uint32_t stage_bytes = (uint32_t)p.TPS * WSTAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.SB * stage_bytes);
   uint64_t* fullB = bars;                       // [RS_SB_MAX]
@@ -298,12 +305,13 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
             } else {
             // Group 0 reads operand rows of tiles 0 .. G0N (one tile of halo), group 1 the rest: every tile's "ready" phase is waited
             // exactly once per conv, before the next phase of that tile can complete (it needs this conv's MMAs).
+            constexpr int G0WAIT = INDEP ? G0N : (G0N + 1 < MT ? G0N + 1 : MT);   // independent tiles need no neighbour's epilogue
 #pragma unroll
-            for (int m = 0; m < (G0N + 1 < MT ? G0N + 1 : MT); m++) mbar_wait(&rowsReady[m], ev & 1);
+            for (int m = 0; m < G0WAIT; m++) mbar_wait(&rowsReady[m], ev & 1);
             tc_fence_after();
             issue_group(std::integral_constant<int, 0>{}, std::integral_constant<int, G0N>{}, cv, slab16);
 #pragma unroll
-            for (int m = G0N + 1; m < MT; m++) mbar_wait(&rowsReady[m], ev & 1);
+            for (int m = G0WAIT; m < MT; m++) mbar_wait(&rowsReady[m], ev & 1);
             tc_fence_after();
             issue_group(std::integral_constant<int, G0N>{}, std::integral_constant<int, MT - G0N>{}, cv, slab16);
             ev++;
@@ -322,24 +330,30 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
     const bool io = warp == 2 && lane == 0;                 // issues every tensor-map copy (bulk groups are per thread)
     uint32_t acc_phase = 0, round_phase = 0;
     bool stores_pending = false;
+    // first slab row of tile m of an item starting at output row t0
+    auto tile_g0 = [&](int t0, int m) { return INDEP ? t0 + m * VT - p.H : t0 - p.H + m * 128; };
+    auto load_item = [&](int it) {                          // io thread: the item's fp32 input boxes -> XT
+      const int bb = it / p.tiles_per_b, tt = (it - bb * p.tiles_per_b) * p.TILE;
+      mbar_expect_tx(xLoaded, (uint32_t)(MT * NH) * XBOX);
+#pragma unroll
+      for (int hh = 0; hh < NH; hh++)
+#pragma unroll
+        for (int m = 0; m < MT; m++) tma_load_3d(xt + (size_t)(hh * MT + m) * XBOX, &tmx, hh * 32, tile_g0(tt, m), bb, xLoaded);
+    };
+    if (INDEP && io && (int)blockIdx.x < p.n_items) load_item(blockIdx.x);
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int b = item / p.tiles_per_b;
       const int t0 = (item - b * p.tiles_per_b) * p.TILE;
       for (int j = 0; j < p.n_kernels; j++) {
         // ---- input: TMA boxes of x -> XT (idle: the last conv that read it has retired), then residual stream -> TMEM, lrelu(x) -> XA
         if (io) {
-          mbar_expect_tx(xLoaded, (uint32_t)(MT * NH) * XBOX);
-#pragma unroll
-          for (int hh = 0; hh < NH; hh++)
-#pragma unroll
-            for (int m = 0; m < MT; m++) tma_load_3d(xt + (size_t)(hh * MT + m) * XBOX, &tmx, hh * 32, t0 - p.H + m * 128, b, xLoaded);
-          if (stores_pending) tma_wait_reads();             // previous round's result boxes have been read out of XA
+          if (!INDEP) load_item(item);                      // (INDEP: prefetched while the previous item finished)
+          if (stores_pending) tma_wait_reads();             // previous result boxes have been read out of their staging area
           mbar_arrive(xaFree);
         }
         stores_pending = true;
         mbar_wait(xLoaded, round_phase);
-        mbar_wait(xaFree, round_phase);
-        round_phase ^= 1;
+        if (!INDEP) mbar_wait(xaFree, round_phase);         // (INDEP: the staging area is separate; waited before it is rewritten)
 #pragma unroll 1
         for (int m = 0; m < MT; m++) {
           const int r128 = q * 32 + lane, row = m * 128 + r128;
@@ -378,13 +392,16 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
             for (int gi = 0; gi < NG; gi++)
 #pragma unroll
               for (int k4 = 0; k4 < 4; k4++) bias[gi][k4] = __ldg(reinterpret_cast<const float4*>(cv.b + col0 + gi * 16) + k4);
+            if (INDEP && c2 == 1 && last) mbar_wait(xaFree, round_phase);   // the previous item's result boxes have left the staging area
 #pragma unroll 1
             for (int m = 0; m < MT; m++) {
-              const int row = m * 128 + q * 32 + lane;
-              const int g = t0 - p.H + row;
+              const int r128 = q * 32 + lane, row = m * 128 + r128;
+              const int g = tile_g0(t0, m) + r128;
               const bool in = g >= 0 && g < p.N;
               mbar_wait(&accFull[m], acc_phase);
               tc_fence_after();
+              if (INDEP && io && c2 == 1 && last && m == MT - 1 && item + (int)gridDim.x < p.n_items)
+                load_item(item + gridDim.x);           // every MMA that read XT has retired: prefetch the next item's input boxes
 #pragma unroll
               for (int gi = 0; gi < NG; gi++) {
                 const int cc = col0 + gi * 16;
@@ -417,11 +434,12 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
 #pragma unroll
                     for (int k = 0; k < 16; k++) v[k] = in ? rs_lrelu(v[k]) : 0.f;
                     rs_store16(xa + (size_t)(cc >> 4) * KBLK, CHUNK, row, v);
-                  } else if (row >= p.H && row < p.H + p.TILE) {
-                    // result of this kernel size, alpha * x (mean over kernel sizes, models.py:154-160): staged in XA (idle: conv1 of
-                    // this pair has retired) as swizzled [OBOX rows][32 channels] boxes for the TMA store / reduce-add
-                    const int ro = row - p.H, bx = ro / p.OBOX, rb_ = ro - bx * p.OBOX;
-                    unsigned char* obox = xa + (size_t)((cc >> 5) * p.n_oboxes + bx) * ((size_t)p.OBOX * 128);
+                  } else if (INDEP ? (r128 >= p.H && r128 < p.H + VT) : (row >= p.H && row < p.H + p.TILE)) {
+                    // result of this kernel size, alpha * x (mean over kernel sizes, models.py:154-160): staged (XA, idle since conv1 of
+                    // this pair has retired; INDEP: the separate staging area) as swizzled [OBOX rows][32 channels] boxes for the TMA
+                    // store / reduce-add
+                    const int ro = INDEP ? r128 - p.H : row - p.H, bx = INDEP ? m : ro / p.OBOX, rb_ = INDEP ? ro : ro - bx * p.OBOX;
+                    unsigned char* obox = (INDEP ? stg : xa) + (size_t)((cc >> 5) * p.n_oboxes + bx) * ((size_t)p.OBOX * 128);
                     const int c16 = (cc & 31) >> 2;
 #pragma unroll
                     for (int k4 = 0; k4 < 4; k4++)
@@ -443,14 +461,15 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
             acc_phase ^= 1;
           }
         }
+        round_phase ^= 1;
         // ---- result boxes -> y: store for the first kernel size, reduce-add (in L2) for the others; rows beyond N are clipped by the TMA
         fence_proxy_async();
         row_warps_sync<32 * NRW>();
         if (io) {
-          tma_wait_all();        // the previous kernel size's boxes are complete in L2 before this one's reduce-add (a round earlier: no wait in practice)
+          if (!INDEP) tma_wait_all();   // the previous kernel size's boxes are complete in L2 before this one's reduce-add (a round earlier: no wait in practice)
           for (int hh = 0; hh < NH; hh++)
             for (int bx = 0; bx < p.n_oboxes; bx++) {
-              const unsigned char* src = xa + (size_t)(hh * p.n_oboxes + bx) * ((size_t)p.OBOX * 128);
+              const unsigned char* src = (INDEP ? stg : xa) + (size_t)(hh * p.n_oboxes + bx) * ((size_t)p.OBOX * 128);
               if (j == 0 && !p.accumulate) tma_store_3d(&tmy, hh * 32, t0 + bx * p.OBOX, b, src);
               else tma_reduce_add_3d(&tmy, hh * 32, t0 + bx * p.OBOX, b, src);
             }
@@ -470,13 +489,14 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------ host side
-static size_t rs_smem_bytes(int C, int MT, int SB, int TPS) {
+static size_t rs_smem_bytes(int C, int MT, int SB, int TPS, bool indep) {
   const size_t slab = (size_t)(C / 16) * 4 * (MT * 128) * 16;
-  return RS_GUARD + 2 * slab + (size_t)SB * TPS * 64 * C + (2 * RS_SB_MAX + 10) * 8 + 16 + 1024;   // + worst-case 1024-byte alignment slack
+  return RS_GUARD + (indep ? 3 : 2) * slab + (size_t)SB * TPS * 64 * C + (2 * RS_SB_MAX + 10) * 8 + 16 + 1024;   // + worst-case 1024-byte alignment slack
 }
 
-// Launch plan (pure host logic): out[11] = {MT, H (halo rows per side), TILE (output rows per work item), work items, grid, weight ring
-// stages, dynamic shared memory bytes, TMEM columns, rows per output box, output boxes per tile and 32-channel block, taps per weight stage}
+// Launch plan (pure host logic): out[12] = {MT, H (halo rows per side), TILE (output rows per work item), work items, grid, weight ring
+// stages, dynamic shared memory bytes, TMEM columns, rows per output box, output boxes per tile and 32-channel block, taps per weight stage,
+// independent-tile mode}
 int resstack_plan(const fs2_resstack_args* a, int num_sms, int* out) {
   if (!a || a->B <= 0 || a->N <= 0 || num_sms <= 0) return FS2_ERR_ARG;
   if (a->C != 32 && a->C != 64) return FS2_ERR_UNSUPPORTED;
@@ -493,27 +513,36 @@ int resstack_plan(const fs2_resstack_args* a, int num_sms, int* out) {
     }
     H = hj > H ? hj : H;
   }
-  H = (H + 3) & ~3;                             // TILE = MT*128 - 2H is then a multiple of 8 (whole swizzle atoms per output box)
-  const int MT = a->C == 32 ? 4 : 3;            // slab rows = MT*128: bounded by shared memory (two slabs of 4*C bytes per row)
-  // the result leaves as TMA boxes of `obox` rows (a multiple of 8, <= 256) that tile TILE exactly: widen the halo by up to 32 rows
-  // until TILE splits into at most 12 boxes (e.g. 384 - 2*4 = 376 = 47 x 8 would need 47 stores; 384 - 2*8 = 368 = 2 x 184)
-  int TILE = 0, obox = 0;
-  for (int hc = H; hc <= H + 32 && !obox; hc += 4) {
-    const int tile = MT * 128 - 2 * hc;
-    if (tile < 64) break;
-    for (int r = 256; r >= 8; r -= 8)
-      if (tile % r == 0 && tile / r <= 12) { TILE = tile; obox = r; H = hc; break; }
+  H = (H + 3) & ~3;                             // output boxes are whole swizzle atoms (multiples of 8 rows)
+  // One kernel size with a small receptive radius on 32 channels: independent 128-row tiles, each with its own halo, the next work
+  // item's input prefetched.  Measured (profiles/r02/pair_bench_indep.txt): 32 channels k = 3: 380 us against 476 us for the shared-halo
+  // slab; 64 channels: no gain at k = 3 (549 / 556 us), a loss from k = 7 on (the per-tile halo recompute outweighs the overlap).
+  const bool indep = a->n_kernels == 1 && a->C == 32 && H <= 16;
+  const int MT = a->C == 32 ? 4 : 3;   // bounded by shared memory (slabs of 4*C bytes per row)
+  int TILE = 0, obox = 0, n_oboxes = 0;
+  if (indep) {
+    obox = 128 - 2 * H; n_oboxes = MT; TILE = MT * obox;
+  } else {
+    // the result leaves as TMA boxes of `obox` rows (a multiple of 8, <= 256) that tile TILE exactly: widen the halo by up to 32 rows
+    // until TILE splits into at most 12 boxes (e.g. 384 - 2*4 = 376 = 47 x 8 would need 47 stores; 384 - 2*8 = 368 = 2 x 184)
+    for (int hc = H; hc <= H + 32 && !obox; hc += 4) {
+      const int tile = MT * 128 - 2 * hc;
+      if (tile < 64) break;
+      for (int r = 256; r >= 8; r -= 8)
+        if (tile % r == 0 && tile / r <= 12) { TILE = tile; obox = r; H = hc; break; }
+    }
+    if (!obox) return FS2_ERR_UNSUPPORTED;
+    n_oboxes = TILE / obox;
   }
-  if (!obox) return FS2_ERR_UNSUPPORTED;
   const long long tiles_per_b = (a->N + TILE - 1) / TILE, items = tiles_per_b * a->B;
   if (items > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
   const int TPS = a->C == 32 ? 4 : 2;           // taps per weight stage: 8 KB stages (fewer handshakes per MMA; conv_tc measured -10..-25 %)
-  int SB = a->C == 32 ? 8 : 4;
-  while (SB > 2 && rs_smem_bytes(a->C, MT, SB, TPS) > 227 * 1024) SB--;
-  if (rs_smem_bytes(a->C, MT, SB, TPS) > 227 * 1024) return FS2_ERR_UNSUPPORTED;
+  int SB = a->C == 32 && !indep ? 8 : 4;
+  while (SB > 2 && rs_smem_bytes(a->C, MT, SB, TPS, indep) > 227 * 1024) SB--;
+  if (rs_smem_bytes(a->C, MT, SB, TPS, indep) > 227 * 1024) return FS2_ERR_UNSUPPORTED;
   out[0] = MT; out[1] = H; out[2] = TILE; out[3] = (int)items; out[4] = items < num_sms ? (int)items : num_sms; out[5] = SB;
-  out[6] = (int)rs_smem_bytes(a->C, MT, SB, TPS); out[7] = 2 * MT * a->C <= 256 ? 256 : 512; out[8] = obox; out[9] = TILE / obox;
-  out[10] = TPS;
+  out[6] = (int)rs_smem_bytes(a->C, MT, SB, TPS, indep); out[7] = 2 * MT * a->C <= 256 ? 256 : 512; out[8] = obox; out[9] = n_oboxes;
+  out[10] = TPS; out[11] = indep ? 1 : 0;
   return FS2_OK;
 }
 
@@ -549,14 +578,15 @@ int resstack(const fs2_resstack_args* a, cudaStream_t s) {
   int derr = FS2_OK;
   DevState* dv = dev_state(&derr);
   if (!dv) return derr;
-  int plan[11];
+  int plan[12];
   FS2_TRY(resstack_plan(a, dv->num_sms.load(std::memory_order_relaxed), plan));
   if (!dv->fused_ready.load(std::memory_order_acquire)) {
     DevOnce once;
     if (!dv->fused_ready.load(std::memory_order_relaxed)) {
       const int mx = 227 * 1024;
-      cudaError_t e = cudaFuncSetAttribute(resstack_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(resstack_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      cudaError_t e = cudaFuncSetAttribute(resstack_kernel<32, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(resstack_kernel<64, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(resstack_kernel<32, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
       if (e != cudaSuccess) return FS2_ERR_CUDA - (int)e;
       dv->fused_ready.store(true, std::memory_order_release);
     }
@@ -579,8 +609,12 @@ int resstack(const fs2_resstack_args* a, cudaStream_t s) {
   FS2_TRY(make_map(&tmx, a->x, a->B, a->N, a->C, 128));
   FS2_TRY(make_map(&tmy, a->y, a->B, a->N, a->C, p.OBOX));
   prof_before(s);
-  if (a->C == 32) resstack_kernel<32, 4><<<plan[4], 64 + 8 * 32, plan[6], s>>>(tmx, tmy, p);
-  else resstack_kernel<64, 3><<<plan[4], 64 + 8 * 64, plan[6], s>>>(tmx, tmy, p);
+  if (plan[11]) {
+    resstack_kernel<32, 4, true><<<plan[4], 64 + 8 * 32, plan[6], s>>>(tmx, tmy, p);      // (the plan selects it for 32 channels only)
+  } else {
+    if (a->C == 32) resstack_kernel<32, 4, false><<<plan[4], 64 + 8 * 32, plan[6], s>>>(tmx, tmy, p);
+    else resstack_kernel<64, 3, false><<<plan[4], 64 + 8 * 64, plan[6], s>>>(tmx, tmy, p);
+  }
   prof_after(s, 0, flops);
   FS2_LAUNCH_CHECK();
   return FS2_OK;

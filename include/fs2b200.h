@@ -194,8 +194,9 @@ typedef struct fs2_resstack_args {
                       conv pair  y (+)= alpha * (conv_k,1(lrelu(conv_k,d(lrelu(x)))) + x)  -- the per-pair mode of the 64-channel stage */
 } fs2_resstack_args;
 int fs2_resstack(const fs2_resstack_args* a, fs2_stream_t stream);
-/* launch plan (pure host logic): out[11] = {128-row tiles per slab, halo rows per side, output rows per work item, work items, grid,
- * weight ring stages, dynamic shared memory bytes, TMEM columns, rows per output TMA box, output boxes per tile, conv taps per weight stage} */
+/* launch plan (pure host logic): out[12] = {128-row tiles per slab, halo rows per side, output rows per work item, work items, grid,
+ * weight ring stages, dynamic shared memory bytes, TMEM columns, rows per output TMA box, output boxes per tile, conv taps per weight stage,
+ * independent-tile mode (single kernel size with a small halo: every 128-row tile carries its own halo)} */
 int fs2_resstack_plan(const fs2_resstack_args* a, int num_sms, int32_t* out);
 
 /* out[b,t] = t < lens[b] ? (int16) trunc(wav[b,t] * scale) : 0   -- the device half of utils.model.vocoder_infer (utils/model.py:82-90:
