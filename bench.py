@@ -34,6 +34,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sampler-period-ms", type=float, default=100.0, help="clock / power sampling period during the timed region (0 = no sampler; diagnosis only)")
+    ap.add_argument("--sampler-queries", choices=["all", "clocks"], default="all", help="'clocks': SM clock every sample, power and event reasons every 5th")
+    ap.add_argument("--prime", type=int, default=2, help="untimed calls of the timed function right before each timed region (counted in `warmup`)")
     ap.add_argument("--warm-seconds", type=float, default=1.0, help="minimum wall time of the untimed warm-up (steps are added to --warmup until it is reached)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step")
@@ -64,14 +67,21 @@ import sys, time
 import pynvml as N
 N.nvmlInit()
 h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+period, light = float(sys.argv[3]) / 1e3, sys.argv[4] == "clocks"
 mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
 get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
 out = open(sys.argv[2], "w")
+k = 0
 while True:
-    r = get_reasons(h)
-    out.write("%d,%d,%d,%.1f,%d\n" % (int(sys.argv[1]), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx, N.nvmlDeviceGetPowerUsage(h) / 1000.0, r))
+    t0 = time.perf_counter()
+    full = not light or k % 5 == 0          # "clocks": power and event reasons on every 5th sample only
+    r = get_reasons(h) if full else -1
+    pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0 if full else -1.0
+    c = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+    out.write("%d,%d,%d,%.1f,%d,%.2f\n" % (int(sys.argv[1]), c, mx, pw, r, (time.perf_counter() - t0) * 1e3))
     out.flush()
-    time.sleep(0.1)
+    k += 1
+    time.sleep(period)
 """
 
 
@@ -83,7 +93,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_ms: float = 100.0, queries: str = "all"):
         self.path = os.path.join(tempfile.mkdtemp(), "clocks.csv")
         self.proc, self.mode = None, None
         phys = gpu_index
@@ -95,7 +105,7 @@ class ClockSampler:
                 phys = gpu_index
         try:
             import pynvml  # noqa: F401
-            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_LOOP, str(phys), self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_LOOP, str(phys), self.path, str(period_ms), queries], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             self.mode = "nvml"
         except Exception:
             try:
@@ -115,7 +125,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
+        sm, mx, pw, reasons, qms = [], [], [], set(), []
         try:
             lines = open(self.path).read().splitlines()
         except Exception:
@@ -126,11 +136,14 @@ class ClockSampler:
                 if self.mode == "nvml":
                     if len(parts) < 5:
                         continue
-                    sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
-                    bits = int(parts[4])
+                    sm.append(float(parts[1])); mx.append(float(parts[2]))
+                    pw.append(float(parts[3]) if float(parts[3]) >= 0 else (pw[-1] if pw else 0.0))
+                    bits = max(int(parts[4]), 0)
                     for b, n in self.BITS.items():
                         if bits & b:
                             reasons.add(n)
+                    if len(parts) > 5:
+                        qms.append(float(parts[5]))
                 else:
                     if len(parts) < 8:
                         continue
@@ -144,7 +157,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "sampler": self.mode}
         busy = [c for c, w in zip(sm, pw) if w > 250.0] or sm          # samples taken under load (idle draw is ~150 W)
         return {"sm_mhz": statistics.median(busy), "sm_mhz_min": min(busy), "sm_mhz_last_samples": busy[-4:], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "samples_under_load": len(busy),
-                "reasons": sorted(reasons), "sampler": self.mode}
+                "reasons": sorted(reasons), "sampler": self.mode, "query_ms_max": max(qms) if qms else None}
 
 
 def workload_config(args, world, frames_per_utt):
@@ -286,22 +299,32 @@ def run_ours(args):
         host = tuple(t.pin_memory() for t in (spk, texts, lens))
         return host, tuple(t.to(dev) for t in host), L
 
-    def timed(fn, steps, collective=True):
-        """`steps` calls of fn bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks."""
+    def timed(fn, steps, collective=True, prime=None):
+        """`steps` calls of fn bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks.  `prime` untimed
+        calls of the same fn run right before the opening barrier (they are warm-up steps: the caller adds them to `warmup`), so that
+        the timed region starts from the loop's own steady state and not after a pause of host-side bookkeeping."""
+        prime = args.prime if prime is None else prime
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]      # one event record per step: the per-step spread, for diagnosis
+        gc_was = gc.isenabled()
+        gc.collect()
+        gc.disable()                             # (as timeit does) no cyclic-GC pause on the launching thread inside the timed region
+        last = None
+        for _ in range(prime):
+            last = None
+            last = fn()
         if world > 1 and collective:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = lib.fs2_kernel_launch_count()
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]      # one event record per step: the per-step spread, for diagnosis
-        gc_was = gc.isenabled()
-        gc.collect()
-        gc.disable()                             # (as timeit does) no cyclic-GC pause on the launching thread inside the timed region
+        mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        host = [time.perf_counter()]
         e0.record()
-        last = None
         for i in range(steps):
+            last = None                          # at most one previous result set alive, as in the warm-up
             last = fn()
             marks[i].record()
+            host.append(time.perf_counter())
         e1.record()
         torch.cuda.synchronize()
         if gc_was:
@@ -310,7 +333,10 @@ def run_ours(args):
             dist.barrier()
         each = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         per = sorted(each)
-        timed.spread = {"min": round(per[0], 3), "median": round(per[len(per) // 2], 3), "max": round(per[-1], 3), "slowest_step_index": each.index(per[-1])}
+        slow = each.index(per[-1])
+        timed.spread = {"min": round(per[0], 3), "median": round(per[len(per) // 2], 3), "max": round(per[-1], 3), "slowest_step_index": slow,
+                        "slowest_step_host_ms": round((host[slow + 1] - host[slow]) * 1e3, 3),
+                        "cudaMallocs_in_region": int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0)}
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         launches = torch.tensor([lib.fs2_kernel_launch_count() - n0], device=dev, dtype=torch.int64)
         if world > 1 and collective:
@@ -357,7 +383,7 @@ def run_ours(args):
     # Warm-up: at least `--warmup` (>= 3) steps AND at least ~1 s of work, so that the first timed region does not sit on the clock /
     # power ramp of a cold GPU (observed: a region timed right after 3 steps of a fresh process can read 20 % slow).  The clock
     # sampler starts before the warm-up so that its own start-up is not inside the timed region either.
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, args.sampler_period_ms, args.sampler_queries) if rank == 0 and args.sampler_period_ms > 0 else None
     warm_steps = max(args.warmup, 3)
     out, wav = step_device()                          # first call: one-time weight packing / workspace allocation
     torch.cuda.synchronize()
@@ -378,9 +404,11 @@ def run_ours(args):
     frames_step = int(all_sum(float(out[9].sum().item())))          # all ranks, one step
     samples_step = frames_step * HOP
     fs2_flop_step = all_sum(fs2_flops_batch(lens_h.tolist(), out[9].tolist()))
+    d2h = int(wav.numel() * 4 + out[9].numel() * 8)
+    del out, wav                                      # (timed() keeps at most one previous result set alive, like the warm-up loop)
 
     # N > 1: the asynchronous gather of the last step completes inside the timed region (flush before the closing event)
-    ms_total, launches, _ = timed(step_device, args.steps) if gather is None else _timed_with_flush(timed, step_device, gather, args.steps)
+    ms_total, launches, _ = timed(step_device, args.steps) if gather is None else _timed_with_flush(timed, step_device, gather, args.steps, args.prime)
     clocks = sampler.stop() if sampler else None
     spread_device = dict(timed.spread)
     value = samples_step * args.steps / (ms_total * 1e-3)
@@ -388,13 +416,10 @@ def run_ours(args):
     ms_mel, _, _ = timed(lambda: model(spk, texts, lens, L), args.steps)
     mel_fps = frames_step * args.steps / (ms_mel * 1e-3)
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps) if gather is None else _timed_with_flush(timed, step_e2e, gather, args.steps)
+    ms_e2e, _, _ = timed(step_e2e, args.steps) if gather is None else _timed_with_flush(timed, step_e2e, gather, args.steps, args.prime)
     e2e_value = samples_step * args.steps / (ms_e2e * 1e-3)
     spread_e2e = dict(timed.spread)
     h2d = spk_h.numel() * 8 + texts_h.numel() * 8 + lens_h.numel() * 8
-    d2h = int(wav.numel() * 4 + out[9].numel() * 8)
 
     def class_profile(fn):
         """One extra, untimed pass with CUDA events around every launch: per-class ms / flops / launches (fs2_profile_begin/end)."""
@@ -428,8 +453,9 @@ def run_ours(args):
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic, traffic_src = tj.get("tcgen05_class_dram_bytes_per_launch"), tj.get("source")
-        roof = {"kernel": "tcgen05 kernel class: conv_tc_kernel (implicit-GEMM conv1d: FFT-block projections / conv-FFN, attention GEMMs, PostNet, HiFi-GAN "
-                          "convs) + resstack_kernel (fused ResBlock group); fp32 CUDA-core convs (encoder, predictors) are NOT counted",
+        roof = {"kernel": "tcgen05 kernel class: conv_tc_kernel (implicit-GEMM conv1d: FFT-block projections / conv-FFN of encoder and decoder, "
+                          "variance predictors, PostNet, HiFi-GAN convs) + resstack_kernel (fused ResBlock group / pairs); attention, layer norm "
+                          "and the few fp32 CUDA-core launches are separate classes (other_classes_ms) and NOT counted",
                 "bound": "tensor", "achieved": r["achieved"], "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": r["frac"],
                 "peak_source": pk["source"] + ", bf16 sustained (kernels timed inside a long step); two MMAs per useful MMA-equivalent in the "
                                               "f16+f8 operand split, three in the split-fp16 one: 0.50 / 0.33 of the peak is the ceiling",
@@ -508,7 +534,7 @@ def run_ours(args):
                 cpu["full_batch_once"] = {"value": sps_f, "unit": "samples/s", "utterances": args.batch, "mel_frames": frames_f, "seconds": sec_f,
                                           "cores": cores_f, "note": "the WHOLE configs[2] batch, one cold pass (no warm-up), same port"}
         line = {"metric": "audio_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": warm_steps, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": warm_steps + args.prime, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world, frames_step / (args.batch * world)),
                 "clocks": clocks,
@@ -530,14 +556,14 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _timed_with_flush(timed, step, gather, steps):
+def _timed_with_flush(timed, step, gather, steps, prime):
     """Timed region for N > 1: the asynchronous rank-0 gather of the LAST step must complete inside the region."""
     count = {"i": 0}
 
     def fn():
         r = step()
         count["i"] += 1
-        if count["i"] == steps:
+        if count["i"] == steps + prime:         # (timed() first makes `prime` untimed calls)
             gather.flush()
         return r
     return timed(fn, steps)

@@ -65,6 +65,18 @@ def patch_vocoder_infer() -> bool:
     return True
 
 
+def patch_text_dataset() -> bool:
+    """Bind `dataset.TextDataset` of the (importable) reference tree to `fastspeech2_b200.frontend.TextDataset`: `synthesize.py` imports the
+    name at start-up (synthesize.py:12) and hands the instance and its `collate_fn` to a stock `DataLoader` (synthesize.py:193-198)."""
+    try:
+        import dataset as ref_dataset
+    except Exception:
+        return False
+    from .frontend import TextDataset
+    ref_dataset.TextDataset = TextDataset
+    return True
+
+
 def main(argv=None) -> None:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
@@ -74,6 +86,7 @@ def main(argv=None) -> None:
     sys.argv = [script] + argv[1:]
     sys.path.insert(0, os.path.dirname(script))       # the reference resolves `utils`, `text`, `dataset` relative to itself
     patch_vocoder_infer()
+    patch_text_dataset()
     runpy.run_path(script, run_name="__main__")
 
 

@@ -63,3 +63,33 @@ print("factories ok", sum(p.numel() for p in m.parameters()), sum(p.numel() for 
 ''' % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "factories ok 35159361 13926017" in r.stdout, r.stdout + r.stderr
+
+
+def test_patch_text_dataset_rebinds_the_reference_name():
+    """`synthesize.py:14` does `from dataset import TextDataset`: after dropin.patch_text_dataset() that name is the batch front-end's
+    class, and the stock DataLoader line of synthesize.py:193-198 runs on it."""
+    import pytest
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    code = r'''
+import sys, os
+sys.path.insert(0, %r)
+from oracle import ref_import
+ref_import._stub()
+REF = ref_import.REFERENCE_ROOT
+sys.path.insert(0, REF); os.chdir(REF)
+import fastspeech2_b200.dropin as d
+assert d.patch_text_dataset()
+from dataset import TextDataset
+assert TextDataset.__module__ == "fastspeech2_b200.frontend"
+import yaml
+from torch.utils.data import DataLoader
+pc = yaml.safe_load(open("config/LJSpeech/preprocess.yaml"))
+ds = TextDataset("preprocessed_data/LJSpeech/val.txt", pc)
+b = next(iter(DataLoader(ds, batch_size=8, collate_fn=ds.collate_fn)))
+assert len(b) == 6 and b[3].shape == (8, b[5])
+print("ok")
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
