@@ -103,6 +103,45 @@ def test_tcgen05_launch_plan_respects_the_hardware_limits():
     assert _plan(h, 1, 4096, 16, 16, 11, 30)[0] == -2
 
 
+def test_fused_resblock_plan_respects_the_hardware_limits():
+    """fs2_resstack_plan (pure host logic) over the shipped generator's kernel / dilation sets, every single-pair shape and a sweep of
+    lengths: the halo covers the receptive radius, the output boxes tile the work item exactly in whole swizzle atoms, shared memory and
+    TMEM stay inside the SM's budget, and the independent-tile mode is chosen exactly where it was measured to pay."""
+    h = _lib.lib()
+
+    def plan(C, N, ks, dils, B=16):
+        a = _lib.ResstackArgs(B=B, N=N, C=C, n_kernels=len(ks), n_dil=len(dils[0]))
+        for j, k in enumerate(ks):
+            a.k[j] = k
+            for d, dv in enumerate(dils[j]):
+                a.dil[j][d] = dv
+        out = (ctypes.c_int32 * 12)()
+        rc = h.fs2_resstack_plan(ctypes.byref(a), 148, out)
+        keys = ("MT", "H", "TILE", "items", "grid", "SB", "smem", "tmem_cols", "obox", "n_oboxes", "TPS", "indep")
+        return rc, dict(zip(keys, out))
+
+    cases = [(C, N, (3, 7, 11), ((1, 3, 5),) * 3) for C in (32, 64) for N in (1, 50, 392, 1000, 129536, 259072)]
+    cases += [(C, N, (k,), ((d,),)) for C in (32, 64) for N in (40, 1000, 259072) for k in (3, 5, 7, 11) for d in (1, 3, 5)]
+    cases += [(C, 5000, (3,), ((1, 3, 5),)) for C in (32, 64)] + [(64, 50, (3, 5), ((1, 2), (2, 6)))]
+    for C, N, ks, dils in cases:
+        rc, p = plan(C, N, ks, dils)
+        assert rc == 0, (C, N, ks, dils, rc)
+        radius = max(sum((k - 1) * d // 2 + (k - 1) // 2 for d in dd) for k, dd in zip(ks, dils))
+        assert p["H"] >= radius and p["H"] % 4 == 0
+        assert p["obox"] % 8 == 0 and 8 <= p["obox"] <= 256 and p["n_oboxes"] * p["obox"] == p["TILE"] and p["n_oboxes"] <= 12
+        if p["indep"]:
+            assert C == 32 and len(ks) == 1 and p["H"] <= 16 and p["obox"] == 128 - 2 * p["H"] and p["n_oboxes"] == p["MT"]
+        else:
+            assert p["TILE"] == p["MT"] * 128 - 2 * p["H"]
+        assert p["indep"] == int(C == 32 and len(ks) == 1 and (radius + 3) // 4 * 4 <= 16)
+        assert p["smem"] <= 227 * 1024 and 2 * p["MT"] * C <= p["tmem_cols"] <= 512
+        assert 2 <= p["SB"] <= 8 and p["TPS"] * 64 * C == 8192
+        assert p["items"] == 16 * -(-N // p["TILE"]) and p["grid"] == min(p["items"], 148)
+    # refused: other widths, even kernels, taps reaching more than 32 rows outside a tile, table overflow
+    assert plan(128, 1000, (3,), ((1,),))[0] == -2 and plan(32, 1000, (4,), ((1,),))[0] == -2
+    assert plan(32, 1000, (11,), ((7,),))[0] == -2 and plan(32, 0, (3,), ((1,),))[0] == -1
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "fastspeech2_b200")
     for dirpath, _, files in os.walk(pkg):
