@@ -35,7 +35,6 @@
 namespace fs2 {
 
 constexpr int RS_MAXK = FS2_MAX_DIL + 4;   // kernel sizes per stage
-constexpr int RS_THREADS_MAX = 64 + 16 * 32;   // producer + MMA warps, up to 16 row warps
 constexpr int RS_GUARD = 1024;             // zeroed bytes in front of the first slab (taps reach up to 32 rows before row 0)
 constexpr int RS_SB_MAX = 16;
 
@@ -133,11 +132,8 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
   // tiles in the first MMA group.  The next conv's first group needs the epilogues of tiles 0 .. G0N: with a 3-tile slab {0} | {1,2}
   // lets it start after ONE tile's epilogue beyond the MMAs ({0,1} | {2} needed all three); with 4 tiles {0,1} | {2,3}.
   constexpr int G0N = INDEP ? MT / 2 : (MT == 3 ? 1 : 2);
-  // Alternative kept for experiments: with 32 channels a whole conv's weight stages fit in the ring, so they can be streamed ONCE and
-  // the MMAs issued tile by tile (tile m of the next conv starts as soon as tiles m-1 .. m+1 are through their epilogue).  Measured
-  // slower than the two-group schedule (6.43 vs 5.67 ms on the 32-channel stage, profiles/r02/resstack_bench_*.txt): the single
-  // issuing thread pays the per-stage bookkeeping four times per conv instead of twice.
-  constexpr bool RESIDENT = false;
+  // (Tried and dropped: streaming a conv's weight stages ONCE and issuing the MMAs tile by tile -- 6.43 vs 5.67 ms on the 32-channel stage,
+  // profiles/r02/resstack_bench_*.txt: the single issuing thread pays the per-stage bookkeeping four times per conv instead of twice.)
   constexpr uint32_t CHUNK = (uint32_t)R * 16, PLANE = 2 * CHUNK, KBLK = 2 * PLANE, SLAB = KB * KBLK;
   constexpr uint32_t WSTAGE = 64u * C;
   constexpr uint32_t TMEM_COLS = (2 * MT * C) <= 256 ? 256 : 512;
@@ -190,7 +186,7 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
           for (int d = 0; d < p.n_dil; d++)
             for (int c2 = 0; c2 < 2; c2++) {
               const RsConv cv = p.conv[j][d][c2];
-              for (int grp = 0; grp < (RESIDENT ? 1 : 2); grp++) {
+              for (int grp = 0; grp < 2; grp++) {       // the weights are streamed once per tile group
                 const unsigned char* src = cv.w + TC_HDR;   // tiles are ordered [kb][tap]: the taps of one K-block are contiguous
                 for (int kb = 0; kb < KB; kb++)
                   for (int tap = 0; tap < cv.taps; tap += p.TPS) {
@@ -255,54 +251,6 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
           for (int c2 = 0; c2 < 2; c2++) {
             const RsConv cv = p.conv[j][d][c2];
             const uint32_t slab16 = c2 == 0 ? xa16 : xt16;
-            if constexpr (RESIDENT) {
-              // Every tile's "ready" phase is waited exactly once per conv (tile m before the MMAs of tile max(m-1, 0)), before the
-              // next phase of that tile can complete (it needs this conv's MMAs of that tile).
-              const int pad = (cv.taps - 1) * cv.dil / 2;
-              const Ring r0 = rb;                          // ring position of this conv's first weight stage
-              int waited = 0;
-#pragma unroll 1
-              for (int m = 0; m < MT; m++) {
-                const int need = m + 2 < MT ? m + 2 : MT;
-                for (; waited < need; waited++) mbar_wait(&rowsReady[waited], ev & 1);
-                tc_fence_after();
-                Ring r = r0;
-                for (int kb = 0; kb < KB; kb++) {
-                  const uint64_t a_hi = a_const | (uint64_t)((slab16 + kb * (KBLK >> 4)) & 0x3fff);
-                  int row_off = -pad + m * 128;
-                  for (int tap = 0; tap < cv.taps; tap += p.TPS, r.advance((uint32_t)p.SB)) {
-                    const int n = min(p.TPS, cv.taps - tap);
-                    if (m == 0) {                          // the stage stays in the ring for the other tiles
-                      mbar_wait(&fullB[r.idx], r.phase);
-                      tc_fence_after();
-                    }
-                    if (leader) {
-                      uint64_t b_hi = b_const | (uint64_t)(smem_u32(ring + (size_t)r.idx * stage_bytes) >> 4);
-                      for (int t = 0; t < n; t++, b_hi += WSTAGE >> 4, row_off += cv.dil) {
-                        const uint64_t ah0 = a_hi + (uint64_t)(int64_t)row_off;
-                        tc_mma_f16(tmem + acc_col + m * C, ah0, b_hi, idesc, (kb | tap | t) ? 1u : 0u);
-                        tc_mma_f8(tmem + acc_col + m * C, ah0 + (PLANE >> 4), b_hi + ((2u * C * 16u) >> 4), idesc, 1u);
-                      }
-                    } else {
-                      row_off += n * cv.dil;
-                    }
-                    __syncwarp();
-                  }
-                }
-                if (leader) tc_commit(&accFull[m]);
-                __syncwarp();
-                if (m == MT - 1) {                         // release the conv's stages once its last MMAs retire
-                  Ring q2 = r0;
-                  while (q2.idx != r.idx || q2.phase != r.phase) {
-                    if (leader) tc_commit(&emptyB[q2.idx]);
-                    q2.advance((uint32_t)p.SB);
-                  }
-                  __syncwarp();
-                  rb = r;
-                }
-              }
-              ev++;
-            } else {
             // Group 0 reads operand rows of tiles 0 .. G0N (one tile of halo), group 1 the rest: every tile's "ready" phase is waited
             // exactly once per conv, before the next phase of that tile can complete (it needs this conv's MMAs).
             constexpr int G0WAIT = INDEP ? G0N : (G0N + 1 < MT ? G0N + 1 : MT);   // independent tiles need no neighbour's epilogue
@@ -315,7 +263,6 @@ __global__ void __launch_bounds__(64 + 8 * C, 1) resstack_kernel(const __grid_co
             tc_fence_after();
             issue_group(std::integral_constant<int, G0N>{}, std::integral_constant<int, MT - G0N>{}, cv, slab16);
             ev++;
-            }
           }
         }
         // The round's final epilogue does not signal: a row warp's next arrival on rowsReady[m] is its conversion of the NEXT round's
