@@ -361,8 +361,87 @@ __global__ void __launch_bounds__(CP_ROWS) conv_post_kernel(const fs2_conv_post_
   a.wav[(long long)b * a.T + t] = tanhf(acc);
 }
 
+// The generator's own shape (32 channels, 7 taps, hifigan/models.py:131): no shared memory at all.  Eight lanes own one time row (one
+// float4 of channels each: a warp reads 4 full 128-byte lines per load instruction, each row exactly once per group plus a 6-row halo),
+// the 7 x 4 weights of a lane live in registers, and TAPS sliding accumulators carry the partial sums of the outputs a row contributes to;
+// a finished output is reduced over the 8 lanes by three shuffles and every lane keeps one of 8 consecutive samples, so the stores are
+// full 32-byte sectors.  (The staged kernel above issues two shared-memory loads per FMA and measured 263 us = 2.0 TB/s at
+// B = 16 x 259k samples; this one is bound by the single read of x.)
+constexpr int CPF_BLOCKS = 18;                         // row blocks of TAPS rows per 8-lane group
+template <int TAPS>
+__global__ void __launch_bounds__(256) conv_post_c32_kernel(const fs2_conv_post_args a, int groups_per_batch, long long n_groups) {
+  constexpr int PAD = (TAPS - 1) / 2, ROWS = CPF_BLOCKS * TAPS - 2 * PAD;     // output rows per group (120 for 7 taps: a multiple of 8)
+  static_assert(ROWS % 8 == 0, "full 8-sample stores");
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool live = grp < n_groups;                     // groups past the end run along with an empty row range (full-warp shuffles below)
+  grp = live ? grp : 0;
+  const int b = (int)(grp / groups_per_batch);
+  const int t0 = (int)(grp - (long long)b * groups_per_batch) * ROWS;
+  const int T = live ? a.T : 0;
+  const int tend = min(t0 + ROWS, T);
+  float4 w[TAPS];
+#pragma unroll
+  for (int j = 0; j < TAPS; j++) w[j] = __ldg(reinterpret_cast<const float4*>(a.w + j * 32) + sub);
+  const float bias = __ldg(a.bias), slope = a.in_slope;
+  const float4* xb = reinterpret_cast<const float4*>(a.x) + (long long)b * a.T * 8 + sub;
+  float* wb = a.wav + (long long)b * a.T;
+  float s[TAPS];
+#pragma unroll
+  for (int k = 0; k < TAPS; k++) s[k] = 0.f;
+  float keep = 0.f;
+#pragma unroll 1
+  for (int blk = 0; blk < CPF_BLOCKS; blk++) {
+    const int rb = t0 - PAD + blk * TAPS;
+    float4 x[TAPS];
+#pragma unroll
+    for (int i = 0; i < TAPS; i++) {
+      const int r = rb + i;
+      x[i] = (r >= 0 && r < T) ? __ldg(xb + (long long)r * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < TAPS; i++) {
+      float4 v = x[i];
+      v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+      v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+      // row r feeds outputs r - PAD .. r + PAD; s[k] is the partial sum of output r - PAD + k, which takes tap TAPS - 1 - k of this row
+#pragma unroll
+      for (int k = 0; k < TAPS; k++) {
+        const float4 wj = w[TAPS - 1 - k];
+        s[k] = fmaf(v.x, wj.x, fmaf(v.y, wj.y, fmaf(v.z, wj.z, fmaf(v.w, wj.w, s[k]))));
+      }
+      float tot = s[0];                                 // output r - PAD has received its last row
+#pragma unroll
+      for (int k = 0; k + 1 < TAPS; k++) s[k] = s[k + 1];
+      s[TAPS - 1] = 0.f;
+      tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+      const int t = rb + i - PAD;
+      if (t >= t0 && t < tend) {
+        const int o = (t - t0) & 7;
+        if (o == sub) keep = tot;
+        if (o == 7 || t == tend - 1) {
+          if (sub <= o) wb[t - o + sub] = tanhf(keep + bias);
+        }
+      }
+    }
+  }
+}
+
 int conv_post(const fs2_conv_post_args* a, cudaStream_t s) {
   if (!a || !a->x || !a->w || !a->bias || !a->wav || a->B <= 0 || a->T <= 0 || a->C <= 0 || a->taps <= 0) return FS2_ERR_ARG;
+  if (a->C == 32 && a->taps == 7 && (reinterpret_cast<uintptr_t>(a->x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15u) == 0) {
+    constexpr int ROWS = CPF_BLOCKS * 7 - 6;
+    const int gpb = (a->T + ROWS - 1) / ROWS;
+    const long long n_groups = (long long)gpb * a->B, blocks = (n_groups * 8 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return FS2_ERR_UNSUPPORTED;
+    prof_before(s);
+    conv_post_c32_kernel<7><<<(unsigned)blocks, 256, 0, s>>>(*a, gpb, n_groups);
+    prof_after(s, 3, 2.0 * (double)a->B * a->T * a->taps * a->C);
+    FS2_LAUNCH_CHECK();
+    return FS2_OK;
+  }
   const size_t smem = ((size_t)a->taps * a->C + (size_t)(CP_ROWS + a->taps - 1) * (a->C + 1)) * sizeof(float);
   if (a->C % 4 || smem > 48 * 1024) return FS2_ERR_UNSUPPORTED;
   const int tiles = (a->T + CP_ROWS - 1) / CP_ROWS;

@@ -422,12 +422,17 @@ def test_durations_and_length_regulate(L, d_control):
 
 
 def test_conv_post_and_transpose():
-    x = rnd(2, 700, 32, seed=1)
-    w = rnd(7, 32, seed=2, scale=0.1)
-    b = torch.tensor([0.05])
-    xa = torch.where(x > 0, x, x * 0.01)
-    want = torch.tanh(torch.nn.functional.conv1d(xa.transpose(1, 2), w.t()[None], b, padding=3))[:, 0]
-    got = ops.conv_post(x.to(DEV), w.to(DEV), b.to(DEV), 0.01)
-    assert (got.cpu() - want).abs().max() < 2e-6
+    """lrelu -> Conv1d(C, 1, k) -> tanh (hifigan/models.py:161-163).  C = 32, k = 7 runs the register-resident kernel (8 lanes per row,
+    sliding accumulators, 120 output rows per lane group: lengths around the group and 8-sample store boundaries); anything else the
+    shared-memory kernel."""
+    for B, T, C, k in ((2, 700, 32, 7), (3, 1, 32, 7), (1, 5, 32, 7), (2, 119, 32, 7), (2, 120, 32, 7), (3, 121, 32, 7), (1, 12345, 32, 7),
+                       (5, 963, 32, 7), (2, 300, 16, 5), (2, 130, 32, 3)):
+        x = rnd(B, T, C, seed=1 + T)
+        w = rnd(k, C, seed=2, scale=0.1)
+        b = torch.tensor([0.05])
+        xa = torch.where(x > 0, x, x * 0.01).double()
+        want = torch.tanh(torch.nn.functional.conv1d(xa.transpose(1, 2), w.double().t()[None], b.double(), padding=(k - 1) // 2))[:, 0]
+        got = ops.conv_post(x.to(DEV), w.to(DEV), b.to(DEV), 0.01)
+        assert got.shape == (B, T) and (got.cpu().double() - want).abs().max() < 2e-6, (B, T, C, k)
     m = rnd(3, 80, 45, seed=3)
     assert torch.equal(ops.transpose_bct_to_btc(m.to(DEV)).cpu(), m.transpose(1, 2).contiguous())
