@@ -3,6 +3,7 @@
 Protocol (hard part 2): (A) free-running -- continuous predictions are compared and the discrete
 decisions (durations, hence mel_lens) must match exactly; (B) teacher-forced with the oracle's own decisions so a
 boundary flip cannot hide or fake a mel error.  Bars from BASELINE.json: mel 1e-3, waveform 1e-4 max-abs."""
+import numpy as np
 import pytest
 import torch
 
@@ -384,3 +385,45 @@ def test_synthesize_path_int16_trim_async(lj_configs, parity_log):
     worst = max(int(abs(w.astype("int32") - (ref_wav[i, :len(w)].numpy() * 32768).astype("int16").astype("int32")).max()) for i, w in enumerate(wavs))
     parity_log("synthesize_path_int16", worst_int16_step_vs_oracle=worst)
     assert worst <= 200          # 200 / 32768 = 6e-3: the end-to-end bound test_end_to_end_wav uses (5e-3) plus truncation
+
+
+def test_batch_mode_front_end_feeds_the_gpu_path(lj_configs, parity_log, tmp_path):
+    """`synthesize.py --mode batch` with the front-end of fastspeech2_b200/frontend.py -- a source file in the
+    `val.txt` layout -> length-bucketed batches prepared in the background -> pinned staged upload -> the loop of synthesize.synthesize
+    (synthesize.py:89-108: model(*(batch[2:]), controls), vocoder_infer).  Every batch is compared with the oracle run on the same
+    collated (host) batch; every utterance must come back exactly once with mel_len * hop int16 samples."""
+    import json
+    from fastspeech2_b200 import dropin, frontend
+    pc, mc = lj_configs
+    m, sd = _model(lj_configs, seed=5)
+    gen, hsd = _generator(seed=2)
+    rng = np.random.default_rng(11)
+    n_vocab = sd["encoder.src_word_emb.weight"].shape[0]
+    lines = []
+    for i in range(11):
+        ids = rng.integers(1, n_vocab, size=int(rng.integers(9, 45)))
+        lines.append(f"utt{i:02d}|LJSpeech|{{{' '.join('p%d' % v for v in ids)}}}|raw {i}")
+    src = tmp_path / "val.txt"
+    src.write_text("\n".join(lines) + "\n")
+    pre = tmp_path / "pre"
+    pre.mkdir()
+    (pre / "speakers.json").write_text(json.dumps({"LJSpeech": 0}))
+    fcfg = {"preprocessing": {"text": {"text_cleaners": ["english_cleaners"]}}, "path": {"preprocessed_path": str(pre)}}
+    t2s = lambda text, cleaners: [int(tok[1:]) for tok in text.strip("{}").split()]
+    tb = frontend.TextBatches(str(src), fcfg, batch_size=4, bucket=True, text_to_sequence=t2s, prefetch=2)
+    hop = pc["preprocessing"]["stft"]["hop_length"]
+    host_batches = list(tb)
+    seen = []
+    for k, (batch, host) in enumerate(zip(tb.device_batches(DEV), host_batches)):
+        ids, raw, spk_d, texts_d, lens_d, Lm = batch
+        assert ids == host[0] and spk_d.is_cuda and torch.equal(texts_d.cpu(), torch.from_numpy(host[3]))
+        spk, texts, lens = (torch.from_numpy(host[i]) for i in (2, 3, 4))
+        out, ref = _free_running_then_teacher_forced(m, sd, (spk, texts, lens, int(Lm)), f"batch_mode_front_end_batch{k}", parity_log)
+        with torch.no_grad():
+            out = m(*(batch[2:]), p_control=1.0, e_control=1.0, d_control=1.0)          # the call of synthesize.py:95-100 on the staged tensors
+        wavs = dropin.vocoder_infer(out[1].transpose(1, 2), gen, mc, pc, lengths=out[9] * hop)
+        assert len(wavs) == len(ids)
+        for i, w in enumerate(wavs):
+            assert w.dtype.name == "int16" and w.shape == (int(out[9][i]) * hop,)
+        seen += ids
+    assert sorted(seen) == [f"utt{i:02d}" for i in range(11)] and len(tb) == 3
