@@ -83,3 +83,43 @@ def test_split_conv_transpose_matches_torch():
         yb = E.conv1d(x, wb, None, pad_left=0)
         got = torch.cat([ya, yb], -1).reshape(2, 9 * u, cout)
         assert (got - want).abs().max() < 1e-5
+
+
+def test_conv_post_sliding_window_schedule():
+    """The work decomposition of conv_post_c32_kernel (rowwise.cu), emulated lane for lane: 8 lanes per time row (4 channels each), groups
+    of 18 x 7 input rows = 120 output rows + a 6-row halo, 7 sliding accumulators per lane (accumulator k of row r belongs to output
+    r - 3 + k and takes tap 6 - k), an 8-lane sum when an output has seen its last row, stores in runs of 8 samples.  Must equal
+    lrelu -> Conv1d(32, 1, 7, padding=3) -> tanh (hifigan/models.py:161-163) for lengths around the group and store-run boundaries,
+    with every sample written exactly once."""
+    import numpy as np
+    TAPS, PAD, BLOCKS = 7, 3, 18
+    ROWS = BLOCKS * TAPS - 2 * PAD
+    rng = np.random.default_rng(0)
+    for T in (1, 5, 7, 8, 9, 119, 120, 121, 127, 128, 250, 963):
+        x = rng.standard_normal((T, 32))
+        w = rng.standard_normal((TAPS, 32)) * 0.1
+        xa = np.where(x > 0, x, 0.01 * x)
+        want = np.array([np.tanh(0.05 + sum((xa[t + j - PAD] * w[j]).sum() for j in range(TAPS) if 0 <= t + j - PAD < T)) for t in range(T)])
+        out = np.full(T, np.nan)
+        for g in range((T + ROWS - 1) // ROWS):
+            t0 = g * ROWS
+            tend = min(t0 + ROWS, T)
+            s, keep = np.zeros((8, TAPS)), np.zeros(8)
+            for blk in range(BLOCKS):
+                for i in range(TAPS):
+                    r = t0 - PAD + blk * TAPS + i
+                    v = xa[r].reshape(8, 4) if 0 <= r < T else np.zeros((8, 4))
+                    for k in range(TAPS):
+                        s[:, k] += (v * w[TAPS - 1 - k].reshape(8, 4)).sum(1)
+                    tot = s[:, 0].sum()
+                    s[:, :-1] = s[:, 1:].copy()
+                    s[:, -1] = 0.0
+                    t = r - PAD
+                    if t0 <= t < tend:
+                        o = (t - t0) & 7
+                        keep[o] = tot
+                        if o == 7 or t == tend - 1:
+                            for sub in range(o + 1):
+                                assert np.isnan(out[t - o + sub])
+                                out[t - o + sub] = np.tanh(keep[sub] + 0.05)
+        assert not np.isnan(out).any() and np.abs(out - want).max() < 1e-12, T
