@@ -522,6 +522,12 @@ static int make_map(CUtensorMap* tm, const float* base, int B, int N, int C, int
 int resstack(const fs2_resstack_args* a, cudaStream_t s) {
   if (!a || !a->x || !a->y) return FS2_ERR_ARG;
   if (!aligned16(a->x) || !aligned16(a->y)) return FS2_ERR_ARG;
+  if (a->B <= 0 || a->N <= 0 || a->C <= 0) return FS2_ERR_ARG;
+  {  // not in place: a work item re-reads halo rows of x that its neighbours' results would already have overwritten
+    const unsigned char *xb = reinterpret_cast<const unsigned char*>(a->x), *yb = reinterpret_cast<const unsigned char*>(a->y);
+    const size_t bytes = (size_t)a->B * a->N * a->C * sizeof(float);
+    if (xb < yb + bytes && yb < xb + bytes) return FS2_ERR_ARG;
+  }
   int derr = FS2_OK;
   DevState* dv = dev_state(&derr);
   if (!dv) return derr;

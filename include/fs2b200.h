@@ -182,7 +182,8 @@ int fs2_conv_post(const fs2_conv_post_args* a, fs2_stream_t stream);
  * :96-103):   y = (1/n_kernels) * sum_j R_j(x),   R_j: x <- conv_{k_j,1}( lrelu( conv_{k_j,dil_jd}( lrelu(x) ) + b1 ) ) + b2 + x  for d = 0..n_dil-1,
  * lrelu slope 0.1, "same" zero padding at the utterance ends.  x, y: contiguous [B][N][C], C in {32, 64} (the 64- / 32-channel stages);
  * every intermediate stays in shared / tensor memory (halo recompute), weights are the f16+f8 tiles of the per-layer kernel
- * (FS2_TC_VARIANT_F8 with N = C: pack_conv_tc(w, f8=True)).  (k-1)*dil/2 <= 32 per conv.  Other shapes: FS2_ERR_UNSUPPORTED. */
+ * (FS2_TC_VARIANT_F8 with N = C: pack_conv_tc(w, f8=True)).  (k-1)*dil/2 <= 32 per conv.  Other shapes: FS2_ERR_UNSUPPORTED.
+ * x and y must not overlap (work items re-read halo rows of x): FS2_ERR_ARG. */
 typedef struct fs2_resstack_args {
   const float* x; float* y; int B, N, C;
   int n_kernels, n_dil;

@@ -54,6 +54,10 @@ def test_host_side_argument_checks_need_no_gpu():
     need = h.fs2_decode_workspace_bytes(ctypes.byref(m), 16, 1024)
     assert need > 16 * 1024 * (256 * 4 + 768 + 1024) * 4
     assert h.fs2_encode_workspace_bytes(ctypes.byref(m), 0, 5) == 0
+    r = _lib.ResstackArgs(x=0x10000, y=0x10000 + 64, B=1, N=100, C=32, n_kernels=1, n_dil=1)
+    assert h.fs2_resstack(ctypes.byref(r), None) == -1           # overlapping x / y (the kernel re-reads halo rows of x)
+    r.y = 0x10008
+    assert h.fs2_resstack(ctypes.byref(r), None) == -1           # misaligned y
 
 
 def _plan(h, B, T, Cin, N, taps, dil=1, num_sms=148, x=0x1000, x_row_stride=None):
