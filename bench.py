@@ -231,6 +231,7 @@ def run_reference(args):
                              "sample": f"{n} of the {args.batch} utterances per step ({frames} mel frames), oracle port of the reference "
                                        "(same ATen CPU kernels), fp32, best of {all, half, 32, 16} host threads"},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mel_frames_per_s": sps / HOP,
             "extra": {"mel_frames_per_s_fastspeech2_only": fps}}
     print(json.dumps(line), flush=True)
 
@@ -541,6 +542,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,
+                "mel_frames_per_s": frames_step * args.steps / (ms_total * 1e-3),          # the other half of BASELINE.json's metric, same timed region
                 "roofline": roof, "cpu_baseline": cpu,
                 "extra": {"step_ms_spread": {"device_timed": spread_device, "e2e": spread_e2e, "note": "this rank's per-step CUDA-event durations"},
                           "mel_frames_per_s": frames_step * args.steps / (ms_total * 1e-3),
